@@ -1,0 +1,700 @@
+// Fused LinearAttention (reference /root/reference/dquartic/model/unet1d.py:473-496, wrapped as
+// Residual(PreNorm(.)) at 1017/1068): out = x + RMSNorm_out(W_out . attn(RMSNorm_pre(x)) + b_out).
+//
+// Nothing of size 384 x L is ever materialised: q/k/v are recomputed from the C-channel input tile by tile.
+//   forward : la_stats (per-chunk online-softmax partials of k and of ctx = softmax_L(k) v^T)
+//             -> la_combine (per row: max, sum, ctx[4][32][32]) -> la_out (q softmax, ctx^T q, to_out, norm, +x)
+//   backward: la_bwd_q (d to_out, d ctx partials, d q-path -> d xn_q) -> la_bwd_combine
+//             -> la_bwd_kv (d k-softmax, d v, d xn, RMSNorm_pre backward, + residual gradient)
+// Mapping: 128 threads per CTA, thread j owns q/k/v channel j = (head h = j/32 = its warp, d = j%32); a tile of
+// 32 positions is staged in shared memory as [n][132] rows so that (a) a thread writes its own column without
+// conflicts, (b) the 32x32 per-head contractions read float4 broadcasts, (c) the "(n, head)" transposed phases
+// (softmax over d, projections back to C channels) read float4 rows conflict-free.
+#include "common.cuh"
+
+namespace dq {
+
+constexpr int TP = 32;     // positions per tile
+constexpr int LDS_ = 132;  // padded row stride of the [n][128] staging tiles (floats)
+
+struct LAArgs {
+  const float* x;      // (R, C, L) block input
+  const float* g_pre;  // (C) PreNorm gain
+  const float* wqkv;   // (384, C)
+  const float* wout;   // (C, 128)
+  const float* bout;   // (C)
+  const float* g_out;  // (C)
+  float* part;         // (R, nchunk, 128, 34) forward partials [m, s, ctx[32]]
+  float* ctx;          // (R, 128, 32)  ctx[h*32+d][e]
+  float* ms;           // (R, 128, 2)   max and sum of exp of k over L
+  float* ypre;         // (R, C, L) to_out output before RMSNorm (saved for backward; may be null)
+  float* out;          // (R, C, L)
+  // backward
+  const float* dres;   // (R, C, L) gradient of the block output
+  float* dxnq;         // (R, C, L) scratch: q-path gradient w.r.t. the pre-normed input
+  float* dpart;        // (R, nchunk, 128, 32) partial d ctx
+  float* dctx;         // (R, 128, 32)
+  float* sd;           // (R, 128)   sum_e dctx*ctx
+  float* dx;           // (R, C, L)
+  float* dwqkv;        // (384, C) accumulated
+  float* dwout;        // (C, 128) accumulated
+  float* dbout;        // (C) accumulated
+  float* dg_out;       // (C) accumulated
+  float* dg_pre;       // (C) accumulated
+  int R, L, chunk, nchunk;
+};
+
+// normalise TP positions of row r starting at n0 into xn_s[n][c]; invalid positions give zeros.
+template <int C>
+__device__ __forceinline__ void load_xn_tile(const float* __restrict__ x, const float* __restrict__ g, int r, int L,
+                                             int n0, int nend, float* xn_s, float* inv_s) {
+  if (threadIdx.x < TP) {
+    int n = n0 + threadIdx.x;
+    float v[C];
+    float s2 = 0.f;
+    bool ok = n < nend;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      v[c] = ok ? __ldg(x + ((size_t)r * C + c) * L + n) : 0.f;
+      s2 = fmaf(v[c], v[c], s2);
+    }
+    float inv = 1.f / fmaxf(sqrtf(s2), 1e-12f);
+    float sc = inv * sqrtf((float)C);
+#pragma unroll
+    for (int c = 0; c < C; ++c) xn_s[threadIdx.x * C + c] = v[c] * sc * g[c];
+    if (inv_s) inv_s[threadIdx.x] = inv;
+  }
+}
+
+template <int C>
+__device__ __forceinline__ float dotC(const float (&w)[C], const float* __restrict__ xs) {
+  float a = 0.f;
+  if constexpr (C % 4 == 0) {
+#pragma unroll
+    for (int c4 = 0; c4 < C / 4; ++c4) {
+      float4 t = *reinterpret_cast<const float4*>(xs + c4 * 4);
+      a = fmaf(w[c4 * 4 + 0], t.x, a);
+      a = fmaf(w[c4 * 4 + 1], t.y, a);
+      a = fmaf(w[c4 * 4 + 2], t.z, a);
+      a = fmaf(w[c4 * 4 + 3], t.w, a);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) a = fmaf(w[c], xs[c], a);
+  }
+  return a;
+}
+
+// acc[e] += a * row[e], e in [0,32), row 16-byte aligned in shared memory (broadcast reads)
+__device__ __forceinline__ void axpy32(float (&acc)[32], float a, const float* __restrict__ row) {
+#pragma unroll
+  for (int e4 = 0; e4 < 8; ++e4) {
+    float4 t = *reinterpret_cast<const float4*>(row + e4 * 4);
+    acc[e4 * 4 + 0] = fmaf(a, t.x, acc[e4 * 4 + 0]);
+    acc[e4 * 4 + 1] = fmaf(a, t.y, acc[e4 * 4 + 1]);
+    acc[e4 * 4 + 2] = fmaf(a, t.z, acc[e4 * 4 + 2]);
+    acc[e4 * 4 + 3] = fmaf(a, t.w, acc[e4 * 4 + 3]);
+  }
+}
+__device__ __forceinline__ float dot32(const float (&w)[32], const float* __restrict__ row) {
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int e4 = 0; e4 < 8; ++e4) {
+    float4 t = *reinterpret_cast<const float4*>(row + e4 * 4);
+    a0 = fmaf(w[e4 * 4 + 0], t.x, a0);
+    a1 = fmaf(w[e4 * 4 + 1], t.y, a1);
+    a0 = fmaf(w[e4 * 4 + 2], t.z, a0);
+    a1 = fmaf(w[e4 * 4 + 3], t.w, a1);
+  }
+  return a0 + a1;
+}
+
+// ------------------------------------------------------------------------------------------- forward: stats
+template <int C>
+__global__ void __launch_bounds__(128) la_stats_kernel(LAArgs a) {
+  __shared__ __align__(16) float xn_s[TP * C];
+  __shared__ __align__(16) float v_s[TP * LDS_];
+  const int j = threadIdx.x, h = j >> 5;
+  const int r = blockIdx.y, ch = blockIdx.x;
+  const int n_begin = ch * a.chunk, n_end = min(a.L, n_begin + a.chunk);
+  float wk[C], wv[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    wk[c] = a.wqkv[(size_t)(kHD + j) * C + c];
+    wv[c] = a.wqkv[(size_t)(2 * kHD + j) * C + c];
+  }
+  float m = -INFINITY, s = 0.f;
+  float ctx[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) ctx[e] = 0.f;
+
+  for (int n0 = n_begin; n0 < n_end; n0 += TP) {
+    load_xn_tile<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, nullptr);
+    __syncthreads();
+    float kreg[TP];
+    float tmax = -INFINITY;
+    const int nv = min(TP, n_end - n0);
+#pragma unroll
+    for (int n = 0; n < TP; ++n) {
+      float kv = dotC<C>(wk, xn_s + n * C);
+      float vv = dotC<C>(wv, xn_s + n * C);
+      kv = (n < nv) ? kv : -INFINITY;
+      kreg[n] = kv;
+      tmax = fmaxf(tmax, kv);
+      v_s[n * LDS_ + j] = vv;
+    }
+    float m_new = fmaxf(m, tmax);
+    float f = __expf(m - m_new);  // exp(-inf) = 0 on the first tile
+    s *= f;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) ctx[e] *= f;
+    m = m_new;
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < TP; ++n) {
+      float p = __expf(kreg[n] - m);
+      s += p;
+      axpy32(ctx, p, v_s + n * LDS_ + h * 32);
+    }
+    __syncthreads();
+  }
+  float* po = a.part + (((size_t)r * a.nchunk + ch) * kHD + j) * 34;
+  po[0] = m;
+  po[1] = s;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) po[2 + e] = ctx[e];
+}
+
+__global__ void __launch_bounds__(128) la_combine_kernel(LAArgs a) {
+  const int j = threadIdx.x, r = blockIdx.x;
+  const float* p = a.part + ((size_t)r * a.nchunk * kHD + j) * 34;
+  float M = -INFINITY;
+  for (int ch = 0; ch < a.nchunk; ++ch) M = fmaxf(M, p[(size_t)ch * kHD * 34]);
+  float S = 0.f, ctx[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) ctx[e] = 0.f;
+  for (int ch = 0; ch < a.nchunk; ++ch) {
+    const float* q = p + (size_t)ch * kHD * 34;
+    float f = __expf(q[0] - M);
+    S = fmaf(q[1], f, S);
+#pragma unroll
+    for (int e = 0; e < 32; ++e) ctx[e] = fmaf(q[2 + e], f, ctx[e]);
+  }
+  float inv = 1.f / S;
+  float* co = a.ctx + ((size_t)r * kHD + j) * 32;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) co[e] = ctx[e] * inv;
+  a.ms[((size_t)r * kHD + j) * 2 + 0] = M;
+  a.ms[((size_t)r * kHD + j) * 2 + 1] = S;
+}
+
+// softmax over the 32 channels of each (n, head) of a staged [n][132] tile, in place, times `scale`.
+__device__ __forceinline__ void tile_softmax_d(float* q_s, float scale) {
+  const int n = threadIdx.x & 31, h = threadIdx.x >> 5;
+  float* row = q_s + n * LDS_ + h * 32;
+  float v[32];
+#pragma unroll
+  for (int e4 = 0; e4 < 8; ++e4) {
+    float4 t = *reinterpret_cast<const float4*>(row + e4 * 4);
+    v[e4 * 4] = t.x; v[e4 * 4 + 1] = t.y; v[e4 * 4 + 2] = t.z; v[e4 * 4 + 3] = t.w;
+  }
+  float mx = v[0];
+#pragma unroll
+  for (int e = 1; e < 32; ++e) mx = fmaxf(mx, v[e]);
+  float sm = 0.f;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) { v[e] = __expf(v[e] - mx); sm += v[e]; }
+  float f = scale / sm;
+#pragma unroll
+  for (int e4 = 0; e4 < 8; ++e4)
+    *reinterpret_cast<float4*>(row + e4 * 4) = make_float4(v[e4 * 4] * f, v[e4 * 4 + 1] * f, v[e4 * 4 + 2] * f, v[e4 * 4 + 3] * f);
+}
+
+// ------------------------------------------------------------------------------------------- forward: output
+template <int C>
+__global__ void __launch_bounds__(128) la_out_kernel(LAArgs a) {
+  extern __shared__ float4 dyn_smem4[];
+  float* sm = reinterpret_cast<float*>(dyn_smem4);
+  float* xn_s = sm;                       // TP*C
+  float* q_s = xn_s + TP * C;             // TP*LDS_
+  float* o_s = q_s + TP * LDS_;           // TP*LDS_
+  float* wout_s = o_s + TP * LDS_;        // C*128
+  float* yp_s = wout_s + C * kHD;         // 4*TP*C
+  const int j = threadIdx.x, h = j >> 5, e = j & 31;
+  const int r = blockIdx.y;
+  const int n_begin = blockIdx.x * a.chunk, n_end = min(a.L, n_begin + a.chunk);
+  const float scale = rsqrtf((float)kDimHead);
+  float wq[C], ctxT[32];
+#pragma unroll
+  for (int c = 0; c < C; ++c) wq[c] = a.wqkv[(size_t)j * C + c];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) ctxT[d] = a.ctx[((size_t)r * kHD + h * 32 + d) * 32 + e];
+  for (int i = j; i < C * kHD; i += 128) wout_s[i] = a.wout[i];
+
+  for (int n0 = n_begin; n0 < n_end; n0 += TP) {
+    load_xn_tile<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, nullptr);
+    __syncthreads();
+#pragma unroll 4
+    for (int n = 0; n < TP; ++n) q_s[n * LDS_ + j] = dotC<C>(wq, xn_s + n * C);
+    __syncthreads();
+    tile_softmax_d(q_s, scale);
+    __syncthreads();
+#pragma unroll 4
+    for (int n = 0; n < TP; ++n) o_s[n * LDS_ + j] = dot32(ctxT, q_s + n * LDS_ + h * 32);
+    __syncthreads();
+    {  // y[c][n] partial over the 32 channels of quarter qd
+      const int n = j & 31, qd = j >> 5;
+      float yp[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) yp[c] = 0.f;
+      const float* orow = o_s + n * LDS_ + qd * 32;
+#pragma unroll
+      for (int e4 = 0; e4 < 8; ++e4) {
+        float4 t = *reinterpret_cast<const float4*>(orow + e4 * 4);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          float4 w = *reinterpret_cast<const float4*>(wout_s + c * kHD + qd * 32 + e4 * 4);
+          yp[c] = fmaf(t.x, w.x, fmaf(t.y, w.y, fmaf(t.z, w.z, fmaf(t.w, w.w, yp[c]))));
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) yp_s[(qd * TP + n) * C + c] = yp[c];
+    }
+    __syncthreads();
+    if (j < TP && n0 + j < n_end) {
+      const int n = n0 + j;
+      float y[C];
+      float s2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        y[c] = a.bout[c] + yp_s[(0 * TP + j) * C + c] + yp_s[(1 * TP + j) * C + c] + yp_s[(2 * TP + j) * C + c] +
+               yp_s[(3 * TP + j) * C + c];
+        s2 = fmaf(y[c], y[c], s2);
+      }
+      float sc = sqrtf((float)C) / fmaxf(sqrtf(s2), 1e-12f);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        size_t idx = ((size_t)r * C + c) * a.L + n;
+        if (a.ypre) a.ypre[idx] = y[c];
+        a.out[idx] = fmaf(y[c] * sc, a.g_out[c], __ldg(a.x + idx));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------- backward: q path
+template <int C>
+__global__ void __launch_bounds__(128) la_bwd_q_kernel(LAArgs a) {
+  extern __shared__ float4 dyn_smem4[];
+  float* sm = reinterpret_cast<float*>(dyn_smem4);
+  float* xn_s = sm;                        // TP*C
+  float* dy_s = xn_s + TP * C;             // TP*C
+  float* q_s = dy_s + TP * C;              // TP*LDS_   q_raw -> q_soft*scale -> d q_raw
+  float* do_s = q_s + TP * LDS_;           // TP*LDS_   d out (128 per position) -> t = qs * dqs
+  float* wq_s = do_s + TP * LDS_;          // 128*C
+  float* yp_s = wq_s + kHD * C;            // 4*TP*C
+  float* tsum_s = yp_s + 4 * TP * C;       // TP*4
+  float* acc_s = tsum_s + TP * 4;          // TP*2*C  per-position-lane partials of d g_out, d b_out
+  const int j = threadIdx.x, h = j >> 5, e = j & 31;
+  const int r = blockIdx.y, ch = blockIdx.x;
+  const int n_begin = ch * a.chunk, n_end = min(a.L, n_begin + a.chunk);
+  const float scale = rsqrtf((float)kDimHead);
+  const float sqrtC = sqrtf((float)C);
+  float wq[C], wo[C], dwq[C], dwo[C];
+  float ctxR[32], ctxT[32], dctx[32];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    wq[c] = a.wqkv[(size_t)j * C + c];
+    wo[c] = a.wout[(size_t)c * kHD + j];
+    dwq[c] = 0.f; dwo[c] = 0.f;
+  }
+#pragma unroll
+  for (int d = 0; d < 32; ++d) {
+    ctxR[d] = a.ctx[((size_t)r * kHD + j) * 32 + d];                 // ctx[h][d=j%32][e=d']
+    ctxT[d] = a.ctx[((size_t)r * kHD + h * 32 + d) * 32 + e];        // ctx[h][d'][e=j%32]
+    dctx[d] = 0.f;
+  }
+  for (int i = j; i < kHD * C; i += 128) wq_s[i] = a.wqkv[i];
+  if (j < TP) {
+#pragma unroll
+    for (int c = 0; c < 2 * C; ++c) acc_s[j * 2 * C + c] = 0.f;
+  }
+
+  for (int n0 = n_begin; n0 < n_end; n0 += TP) {
+    load_xn_tile<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, nullptr);
+    if (j < TP) {  // d y = RMSNorm_out backward of d res
+      const int n = n0 + j;
+      const bool ok = n < n_end;
+      float y[C], dr[C];
+      float s2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        size_t idx = ((size_t)r * C + c) * a.L + n;
+        y[c] = ok ? __ldg(a.ypre + idx) : 0.f;
+        dr[c] = ok ? __ldg(a.dres + idx) : 0.f;
+        s2 = fmaf(y[c], y[c], s2);
+      }
+      float nrm = sqrtf(s2);
+      float inv = 1.f / fmaxf(nrm, 1e-12f);
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float uh = y[c] * inv;
+        acc_s[j * 2 * C + c] += dr[c] * uh * sqrtC;
+        float duh = dr[c] * a.g_out[c] * sqrtC;
+        dot = fmaf(duh, uh, dot);
+        y[c] = uh; dr[c] = duh;
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float d = (nrm > 1e-12f) ? (dr[c] - y[c] * dot) * inv : dr[c] * inv;
+        d = ok ? d : 0.f;
+        acc_s[j * 2 * C + C + c] += d;
+        dy_s[j * C + c] = d;
+      }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int n = 0; n < TP; ++n) {
+      q_s[n * LDS_ + j] = dotC<C>(wq, xn_s + n * C);
+      do_s[n * LDS_ + j] = dotC<C>(wo, dy_s + n * C);
+    }
+    __syncthreads();
+    tile_softmax_d(q_s, scale);
+    __syncthreads();
+    float dq[TP];
+#pragma unroll
+    for (int n = 0; n < TP; ++n) {
+      const float qsv = q_s[n * LDS_ + j];
+      const float* drow = do_s + n * LDS_ + h * 32;
+      // dqs = sum_e ctx[j][e] do[e];  dctx[j][e] += qs * do[e]   (same broadcast loads)
+      float dqs0 = 0.f, dqs1 = 0.f;
+#pragma unroll
+      for (int e4 = 0; e4 < 8; ++e4) {
+        float4 t = *reinterpret_cast<const float4*>(drow + e4 * 4);
+        dqs0 = fmaf(ctxR[e4 * 4 + 0], t.x, dqs0);
+        dqs1 = fmaf(ctxR[e4 * 4 + 1], t.y, dqs1);
+        dqs0 = fmaf(ctxR[e4 * 4 + 2], t.z, dqs0);
+        dqs1 = fmaf(ctxR[e4 * 4 + 3], t.w, dqs1);
+        dctx[e4 * 4 + 0] = fmaf(qsv, t.x, dctx[e4 * 4 + 0]);
+        dctx[e4 * 4 + 1] = fmaf(qsv, t.y, dctx[e4 * 4 + 1]);
+        dctx[e4 * 4 + 2] = fmaf(qsv, t.z, dctx[e4 * 4 + 2]);
+        dctx[e4 * 4 + 3] = fmaf(qsv, t.w, dctx[e4 * 4 + 3]);
+      }
+      dq[n] = dqs0 + dqs1;
+      // out[j=(h,e)][n] for d W_out
+      float o = dot32(ctxT, q_s + n * LDS_ + h * 32);
+      const float* dyr = dy_s + n * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) dwo[c] = fmaf(dyr[c], o, dwo[c]);
+    }
+    __syncthreads();  // all reads of do_s done
+#pragma unroll
+    for (int n = 0; n < TP; ++n) do_s[n * LDS_ + j] = q_s[n * LDS_ + j] * dq[n];
+    __syncthreads();
+    {
+      const int n = j & 31, hh = j >> 5;
+      const float* row = do_s + n * LDS_ + hh * 32;
+      float t = 0.f;
+#pragma unroll
+      for (int e4 = 0; e4 < 8; ++e4) {
+        float4 v = *reinterpret_cast<const float4*>(row + e4 * 4);
+        t += (v.x + v.y) + (v.z + v.w);
+      }
+      tsum_s[n * 4 + hh] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < TP; ++n) {
+      float qsv = q_s[n * LDS_ + j];
+      float dqr = qsv * (dq[n] - tsum_s[n * 4 + h] * (1.f / scale));
+      const float* xr = xn_s + n * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) dwq[c] = fmaf(dqr, xr[c], dwq[c]);
+      q_s[n * LDS_ + j] = dqr;  // own column only
+    }
+    __syncthreads();
+    {  // d xn_q[c][n] = sum_j wq[j][c] dqr[j][n]
+      const int n = j & 31, qd = j >> 5;
+      float yp[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) yp[c] = 0.f;
+      const float* qrow = q_s + n * LDS_ + qd * 32;
+#pragma unroll
+      for (int e4 = 0; e4 < 8; ++e4) {
+        float4 t = *reinterpret_cast<const float4*>(qrow + e4 * 4);
+        const float* w0 = wq_s + (qd * 32 + e4 * 4) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          yp[c] = fmaf(t.x, w0[c], fmaf(t.y, w0[C + c], fmaf(t.z, w0[2 * C + c], fmaf(t.w, w0[3 * C + c], yp[c]))));
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) yp_s[(qd * TP + n) * C + c] = yp[c];
+    }
+    __syncthreads();
+    if (j < TP && n0 + j < n_end) {
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        a.dxnq[((size_t)r * C + c) * a.L + n0 + j] = yp_s[(0 * TP + j) * C + c] + yp_s[(1 * TP + j) * C + c] +
+                                                     yp_s[(2 * TP + j) * C + c] + yp_s[(3 * TP + j) * C + c];
+    }
+    __syncthreads();
+  }
+  float* dp = a.dpart + (((size_t)r * a.nchunk + ch) * kHD + j) * 32;
+#pragma unroll
+  for (int d = 0; d < 32; ++d) dp[d] = dctx[d];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    atomicAdd(a.dwqkv + (size_t)j * C + c, dwq[c]);
+    atomicAdd(a.dwout + (size_t)c * kHD + j, dwo[c]);
+  }
+  if (j < 32) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float s1 = warp_sum(acc_s[j * 2 * C + c]), s2 = warp_sum(acc_s[j * 2 * C + C + c]);
+      if (j == 0) { atomicAdd(a.dg_out + c, s1); atomicAdd(a.dbout + c, s2); }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) la_bwd_combine_kernel(LAArgs a) {
+  const int j = threadIdx.x, r = blockIdx.x;
+  float d[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) d[e] = 0.f;
+  for (int ch = 0; ch < a.nchunk; ++ch) {
+    const float* p = a.dpart + (((size_t)r * a.nchunk + ch) * kHD + j) * 32;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) d[e] += p[e];
+  }
+  const float* c = a.ctx + ((size_t)r * kHD + j) * 32;
+  float* o = a.dctx + ((size_t)r * kHD + j) * 32;
+  float sd = 0.f;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) { o[e] = d[e]; sd = fmaf(d[e], c[e], sd); }
+  a.sd[(size_t)r * kHD + j] = sd;
+}
+
+// ------------------------------------------------------------------------------------------- backward: k/v path
+template <int C>
+__global__ void __launch_bounds__(128) la_bwd_kv_kernel(LAArgs a) {
+  extern __shared__ float4 dyn_smem4[];
+  float* sm = reinterpret_cast<float*>(dyn_smem4);
+  float* xn_s = sm;                        // TP*C
+  float* k_s = xn_s + TP * C;              // TP*LDS_
+  float* v_s = k_s + TP * LDS_;            // TP*LDS_
+  float* wk_s = v_s + TP * LDS_;           // 128*C
+  float* wv_s = wk_s + kHD * C;            // 128*C
+  float* yp_s = wv_s + kHD * C;            // 4*TP*C
+  float* inv_s = yp_s + 4 * TP * C;        // TP
+  float* acc_s = inv_s + TP;               // TP*C
+  const int j = threadIdx.x, h = j >> 5, e = j & 31;
+  const int r = blockIdx.y;
+  const int n_begin = blockIdx.x * a.chunk, n_end = min(a.L, n_begin + a.chunk);
+  const float sqrtC = sqrtf((float)C);
+  float wk[C], wv[C], dwk[C], dwv[C];
+  float dcR[32], dcT[32];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    wk[c] = a.wqkv[(size_t)(kHD + j) * C + c];
+    wv[c] = a.wqkv[(size_t)(2 * kHD + j) * C + c];
+    dwk[c] = 0.f; dwv[c] = 0.f;
+  }
+#pragma unroll
+  for (int d = 0; d < 32; ++d) {
+    dcR[d] = a.dctx[((size_t)r * kHD + j) * 32 + d];           // dctx[h][d=j%32][e']
+    dcT[d] = a.dctx[((size_t)r * kHD + h * 32 + d) * 32 + e];  // dctx[h][d'][e=j%32]
+  }
+  for (int i = j; i < kHD * C; i += 128) {
+    wk_s[i] = a.wqkv[(size_t)kHD * C + i];
+    wv_s[i] = a.wqkv[(size_t)2 * kHD * C + i];
+  }
+  const float M = a.ms[((size_t)r * kHD + j) * 2], Sinv = 1.f / a.ms[((size_t)r * kHD + j) * 2 + 1];
+  const float sdj = a.sd[(size_t)r * kHD + j];
+  if (j < TP) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc_s[j * C + c] = 0.f;
+  }
+
+  for (int n0 = n_begin; n0 < n_end; n0 += TP) {
+    load_xn_tile<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, inv_s);
+    __syncthreads();
+    float kown[TP];
+#pragma unroll
+    for (int n = 0; n < TP; ++n) {
+      float kr = dotC<C>(wk, xn_s + n * C);
+      float ks = __expf(kr - M) * Sinv;
+      kown[n] = ks;
+      k_s[n * LDS_ + j] = ks;
+      v_s[n * LDS_ + j] = dotC<C>(wv, xn_s + n * C);
+    }
+    __syncthreads();
+    float dkr[TP], dvr[TP];
+#pragma unroll
+    for (int n = 0; n < TP; ++n) {
+      float dks = dot32(dcR, v_s + n * LDS_ + h * 32);
+      float dv = dot32(dcT, k_s + n * LDS_ + h * 32);
+      float dk = kown[n] * (dks - sdj);
+      dkr[n] = dk; dvr[n] = dv;
+      const float* xr = xn_s + n * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) { dwk[c] = fmaf(dk, xr[c], dwk[c]); dwv[c] = fmaf(dv, xr[c], dwv[c]); }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < TP; ++n) { k_s[n * LDS_ + j] = dkr[n]; v_s[n * LDS_ + j] = dvr[n]; }
+    __syncthreads();
+    {
+      const int n = j & 31, qd = j >> 5;
+      float yp[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) yp[c] = 0.f;
+      const float* krow = k_s + n * LDS_ + qd * 32;
+      const float* vrow = v_s + n * LDS_ + qd * 32;
+#pragma unroll
+      for (int e4 = 0; e4 < 8; ++e4) {
+        float4 tk = *reinterpret_cast<const float4*>(krow + e4 * 4);
+        float4 tv = *reinterpret_cast<const float4*>(vrow + e4 * 4);
+        const float* w0 = wk_s + (qd * 32 + e4 * 4) * C;
+        const float* w1 = wv_s + (qd * 32 + e4 * 4) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          float t = fmaf(tk.x, w0[c], fmaf(tk.y, w0[C + c], fmaf(tk.z, w0[2 * C + c], fmaf(tk.w, w0[3 * C + c], yp[c]))));
+          yp[c] = fmaf(tv.x, w1[c], fmaf(tv.y, w1[C + c], fmaf(tv.z, w1[2 * C + c], fmaf(tv.w, w1[3 * C + c], t))));
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) yp_s[(qd * TP + n) * C + c] = yp[c];
+    }
+    __syncthreads();
+    if (j < TP && n0 + j < n_end) {
+      const int n = n0 + j;
+      float inv = inv_s[j];
+      float uh[C], duh[C];
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        size_t idx = ((size_t)r * C + c) * a.L + n;
+        float dxn = yp_s[(0 * TP + j) * C + c] + yp_s[(1 * TP + j) * C + c] + yp_s[(2 * TP + j) * C + c] +
+                    yp_s[(3 * TP + j) * C + c] + __ldg(a.dxnq + idx);
+        float xv = __ldg(a.x + idx);
+        uh[c] = xv * inv;
+        acc_s[j * C + c] += dxn * uh[c] * sqrtC;
+        duh[c] = dxn * a.g_pre[c] * sqrtC;
+        dot = fmaf(duh[c], uh[c], dot);
+      }
+      // note: inv = 1/max(norm, eps); norm > eps <=> inv < 1e12
+      const bool big = inv < 1e12f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        size_t idx = ((size_t)r * C + c) * a.L + n;
+        float d = big ? (duh[c] - uh[c] * dot) * inv : duh[c] * inv;
+        a.dx[idx] = __ldg(a.dres + idx) + d;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    atomicAdd(a.dwqkv + (size_t)(kHD + j) * C + c, dwk[c]);
+    atomicAdd(a.dwqkv + (size_t)(2 * kHD + j) * C + c, dwv[c]);
+  }
+  if (j < 32) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float s1 = warp_sum(acc_s[j * C + c]);
+      if (j == 0) atomicAdd(a.dg_pre + c, s1);
+    }
+  }
+}
+
+template <int C>
+static int la_fwd_launch(const LAArgs& a, cudaStream_t st) {
+  dim3 grid((unsigned)a.nchunk, (unsigned)a.R);
+  la_stats_kernel<C><<<grid, 128, 0, st>>>(a);
+  DQ_LAUNCH_CHECK();
+  la_combine_kernel<<<(unsigned)a.R, 128, 0, st>>>(a);
+  DQ_LAUNCH_CHECK();
+  {
+    size_t smem = sizeof(float) * (TP * C + 2 * TP * LDS_ + C * kHD + 4 * TP * C);
+    cudaFuncSetAttribute(la_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    la_out_kernel<C><<<grid, 128, smem, st>>>(a);
+  }
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+template <int C>
+static int la_bwd_launch(const LAArgs& a, cudaStream_t st) {
+  dim3 grid((unsigned)a.nchunk, (unsigned)a.R);
+  {
+    size_t smem = sizeof(float) * (2 * TP * C + 2 * TP * LDS_ + kHD * C + 4 * TP * C + TP * 4 + TP * 2 * C);
+    cudaFuncSetAttribute(la_bwd_q_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    la_bwd_q_kernel<C><<<grid, 128, smem, st>>>(a);
+  }
+  DQ_LAUNCH_CHECK();
+  la_bwd_combine_kernel<<<(unsigned)a.R, 128, 0, st>>>(a);
+  DQ_LAUNCH_CHECK();
+  {
+    size_t smem = sizeof(float) * (TP * C + 2 * TP * LDS_ + 2 * kHD * C + 4 * TP * C + TP + TP * C);
+    cudaFuncSetAttribute(la_bwd_kv_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    la_bwd_kv_kernel<C><<<grid, 128, smem, st>>>(a);
+  }
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dq
+
+using namespace dq;
+
+// chunking policy shared by forward and backward (the Python side sizes `part`/`dpart` from dq_la_nchunk)
+static int la_chunk(int L) {
+  int chunk = 2048;
+  if (L <= 2048) chunk = ((L + TP - 1) / TP) * TP;
+  return chunk;
+}
+DQ_API int dq_la_nchunk(int L) { int c = la_chunk(L); return (L + c - 1) / c; }
+
+DQ_API int dq_linattn_fwd(const float* x, const float* g_pre, const float* wqkv, const float* wout, const float* bout,
+                          const float* g_out, float* part, float* ctx, float* ms, float* ypre, float* out, int C,
+                          int R, int L, void* stream) {
+  LAArgs a{};
+  a.x = x; a.g_pre = g_pre; a.wqkv = wqkv; a.wout = wout; a.bout = bout; a.g_out = g_out;
+  a.part = part; a.ctx = ctx; a.ms = ms; a.ypre = ypre; a.out = out;
+  a.R = R; a.L = L; a.chunk = la_chunk(L); a.nchunk = (L + a.chunk - 1) / a.chunk;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (R <= 0 || L <= 0) return 0;
+  switch (C) {
+    case 4: return la_fwd_launch<4>(a, st);
+    case 8: return la_fwd_launch<8>(a, st);
+    case 12: return la_fwd_launch<12>(a, st);
+    case 16: return la_fwd_launch<16>(a, st);
+    case 24: return la_fwd_launch<24>(a, st);
+    case 32: return la_fwd_launch<32>(a, st);
+    default: return -3;
+  }
+}
+
+DQ_API int dq_linattn_bwd(const float* x, const float* dres, const float* ypre, const float* ctx, const float* ms,
+                          const float* g_pre, const float* wqkv, const float* wout, const float* g_out, float* dxnq,
+                          float* dpart, float* dctx, float* sd, float* dx, float* dwqkv, float* dwout, float* dbout,
+                          float* dg_out, float* dg_pre, int C, int R, int L, void* stream) {
+  LAArgs a{};
+  a.x = x; a.dres = dres; a.ypre = const_cast<float*>(ypre); a.ctx = const_cast<float*>(ctx);
+  a.ms = const_cast<float*>(ms); a.g_pre = g_pre; a.wqkv = wqkv; a.wout = wout; a.g_out = g_out;
+  a.dxnq = dxnq; a.dpart = dpart; a.dctx = dctx; a.sd = sd; a.dx = dx; a.dwqkv = dwqkv; a.dwout = dwout;
+  a.dbout = dbout; a.dg_out = dg_out; a.dg_pre = dg_pre;
+  a.R = R; a.L = L; a.chunk = la_chunk(L); a.nchunk = (L + a.chunk - 1) / a.chunk;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (R <= 0 || L <= 0) return 0;
+  switch (C) {
+    case 4: return la_bwd_launch<4>(a, st);
+    case 8: return la_bwd_launch<8>(a, st);
+    case 12: return la_bwd_launch<12>(a, st);
+    case 16: return la_bwd_launch<16>(a, st);
+    case 24: return la_bwd_launch<24>(a, st);
+    case 32: return la_bwd_launch<32>(a, st);
+    default: return -3;
+  }
+}

@@ -1,0 +1,101 @@
+// Fused optimizer step over the FLAT parameter / gradient buffers: global grad-norm (one reduction), clip
+// coefficient on the device (no host sync), AdamW with decoupled weight decay, and the bf16 (+ transposed)
+// operand refresh for the tcgen05 GEMMs (mid.cu: cast_transpose).
+// Replaces (reference /root/reference/dquartic/model/model_interface.py): clip_grad_norm_(max_norm=10) 1121,
+// torch.optim.AdamW(lr) 1011 / optimizer.step() 1122.  Traffic: 4 B/param (norm) + 28 B/param (update).
+#include "common.cuh"
+
+namespace dq {
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long n, double* out) {
+  __shared__ double red[8];
+  const long stride = (long)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  const long n4 = ((((size_t)x) & 15) == 0) ? n / 4 : 0;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int cnt = 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    a0 = fmaf(v.x, v.x, a0); a1 = fmaf(v.y, v.y, a1); a2 = fmaf(v.z, v.z, a2); a3 = fmaf(v.w, v.w, a3);
+    if (++cnt == 64) { acc += (double)a0 + (double)a1 + (double)a2 + (double)a3; a0 = a1 = a2 = a3 = 0.f; cnt = 0; }
+  }
+  acc += (double)a0 + (double)a1 + (double)a2 + (double)a3;
+  for (long i = n4 * 4 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc += (double)x[i] * (double)x[i];
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    atomicAdd(out, t);
+  }
+}
+
+// norm = sqrt(sumsq); coef = min(1, max_norm / (norm + 1e-6))   (torch.nn.utils.clip_grad_norm_)
+__global__ void clip_coef_kernel(const double* sumsq, float max_norm, float* out /* [0]=norm, [1]=coef */) {
+  float norm = (float)sqrt(*sumsq);
+  float coef = max_norm / (norm + 1e-6f);
+  out[0] = norm;
+  out[1] = coef < 1.f ? coef : 1.f;
+}
+
+// torch.optim.AdamW single-tensor arithmetic, grads pre-scaled by the clip coefficient read from device memory.
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v, long n,
+                                                    const float* __restrict__ coef_ptr, float lr, float b1, float b2,
+                                                    float eps, float wd, float step_size, float bc2_sqrt) {
+  const float coef = coef_ptr ? coef_ptr[1] : 1.f;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const float decay = 1.f - lr * wd;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gi = g[i] * coef;
+    float pi = p[i] * decay;
+    float mi = m[i];
+    mi = mi + (gi - mi) * (1.f - b1);  // exp_avg.lerp_(grad, 1 - beta1)
+    float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi = pi - step_size * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ p, float v, long n) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+}  // namespace dq
+using namespace dq;
+
+DQ_API int dq_sumsq(const float* x, long n, double* out, void* stream) {
+  if (n <= 0) return 0;
+  long b = (n + 256L * 32 - 1) / (256L * 32);
+  if (b > 148L * 8) b = 148L * 8;
+  if (b < 1) b = 1;
+  sumsq_kernel<<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+DQ_API int dq_clip_coef(const double* sumsq, float max_norm, float* out, void* stream) {
+  clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, max_norm, out);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+DQ_API int dq_adamw(float* p, const float* g, float* m, float* v, long n, const float* coef_ptr, float lr, float b1,
+                    float b2, float eps, float wd, float step_size, float bc2_sqrt, void* stream) {
+  if (n <= 0) return 0;
+  long b = (n + 256L * 8 - 1) / (256L * 8);
+  if (b > 148L * 16) b = 148L * 16;
+  if (b < 1) b = 1;
+  adamw_kernel<<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, coef_ptr, lr, b1, b2, eps, wd, step_size, bc2_sqrt);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+DQ_API int dq_fill(float* p, float v, long n, void* stream) {
+  if (n <= 0) return 0;
+  long b = (n + 256L * 8 - 1) / (256L * 8);
+  if (b > 148L * 16) b = 148L * 16;
+  fill_kernel<<<(unsigned)b, 256, 0, (cudaStream_t)stream>>>(p, v, n);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}

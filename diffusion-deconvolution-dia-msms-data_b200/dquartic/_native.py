@@ -1,0 +1,141 @@
+"""ctypes binding of the C-ABI in include/dquartic_b200.h (lib/libdquartic_b200.so, sm_100a).
+
+There is no CPU fallback: if the library is missing, or a tensor is not a contiguous CUDA tensor of the expected
+dtype, the call raises.  `launches` counts kernels launched through this module (bench.py reports it).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdquartic_b200.so")
+
+# signature mini-language: p = device pointer (torch tensor / None / int), i = int, l = long, f = float,
+# s = stream (filled in automatically), h = host int array (sequence of python ints)
+_SIGS = {
+    "dq_qsample": ("pppppilis", 1),
+    "dq_mix_affine": ("ppffffpls", 1),
+    "dq_add_mul": ("pffpls", 1),
+    "dq_ddim_step": ("pppffffils", 1),
+    "dq_sample_finalize": ("ppppls", 1),
+    "dq_mse": ("ppppfls", 1),
+    "dq_add_inplace": ("ppls", 1),
+    "dq_conv1d_fwd": ("pipipippiiiiippiipppiiiis", 1),
+    "dq_block_bwd": ("ppppiipppiiiis", 1),
+    "dq_conv1d_bwd_data": ("pppiipiiiiiiiiiis", 1),
+    "dq_conv1d_bwd_weight": ("ppipipippiiiiiiiiis", 1),
+    "dq_sample_dot": ("ppppilis", 1),
+    "dq_linattn_fwd": ("pppppppppppiiis", 3),
+    "dq_linattn_bwd": ("pppppppppppppppppppiiis", 3),
+    "dq_time_embed": ("ppiifs", 1),
+    "dq_linear_fwd": ("ppppiiis", 1),
+    "dq_linear_bwd": ("ppppppiiis", 2),
+    "dq_act_fwd": ("ppils", 1),
+    "dq_act_bwd": ("pppils", 1),
+    "dq_ncl_nlc": ("ppiiiis", 1),
+    "dq_gemm_bf16_tn": ("plllplllliplpiiiiihiilis", 1),
+    "dq_mid_pack": ("ppiiiis", 1),
+    "dq_transpose_bf16": ("ppiils", 1),
+    "dq_cast_transpose": ("pppiis", 1),
+    "dq_rownorm_fwd": ("pippiipppipiiis", 1),
+    "dq_rownorm_bwd": ("pipippiipppipipppiiis", 2),
+    "dq_colsum": ("ppiis", 1),
+    "dq_attn_core_fwd": ("ppppppiis", 1),
+    "dq_attn_core_bwd": ("ppppppppiis", 1),
+    "dq_sumsq": ("plps", 1),
+    "dq_clip_coef": ("pfps", 1),
+    "dq_adamw": ("pppplpfffffffs", 1),
+    "dq_fill": ("pfls", 1),
+    "dq_multiplex": ("ppippffpppppilis", 3),
+}
+_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_long, "f": ctypes.c_float, "s": ctypes.c_void_p,
+       "h": ctypes.POINTER(ctypes.c_int)}
+
+_lib = None
+launches = 0
+calls = 0
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU fallback for the dquartic hot path.")
+        _lib = ctypes.CDLL(LIB_PATH)
+        for name, (sig, _) in _SIGS.items():
+            fn = getattr(_lib, name)
+            fn.restype = ctypes.c_int
+            fn.argtypes = [_CT[c] for c in sig]
+        _lib.dq_la_nchunk.restype = ctypes.c_int
+        _lib.dq_la_nchunk.argtypes = [ctypes.c_int]
+        _lib.dq_gemm_last_error.restype = ctypes.c_int
+        _lib.dq_gemm_last_error.argtypes = []
+    return _lib
+
+
+def exported_symbols():
+    return sorted(list(_SIGS) + ["dq_la_nchunk", "dq_gemm_last_error"])
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if not x.is_cuda:
+        raise NativeError("dquartic_b200 kernels need CUDA tensors (no CPU fallback)")
+    if not x.is_contiguous():
+        raise NativeError("non-contiguous tensor passed to a dquartic_b200 kernel")
+    return x.data_ptr()
+
+
+def call(name, *args):
+    """Launch `name` on torch's current CUDA stream.  Raises on a non-zero return code."""
+    global launches, calls
+    sig, nk = _SIGS[name]
+    fn = getattr(lib(), name)
+    if len(args) != len(sig) - 1:
+        raise TypeError(f"{name}: expected {len(sig) - 1} arguments, got {len(args)}")
+    conv = []
+    keep = []
+    for c, a in zip(sig, args):
+        if c == "p":
+            conv.append(_ptr(a))
+        elif c == "h":
+            arr = (ctypes.c_int * len(a))(*[int(v) for v in a])
+            keep.append(arr)
+            conv.append(arr)
+        elif c == "f":
+            conv.append(float(a))
+        else:
+            conv.append(int(a))
+    conv.append(torch.cuda.current_stream().cuda_stream)
+    rc = fn(*conv)
+    if rc != 0:
+        raise NativeError(f"{name} failed with code {rc}" + (f" ({_cuda_err(rc)})" if rc > 0 else ""))
+    launches += nk
+    calls += 1
+    return rc
+
+
+def _cuda_err(rc):
+    try:
+        from torch.cuda import cudart
+        return str(cudart().cudaGetErrorString(rc))
+    except Exception:
+        return "cuda error"
+
+
+def la_nchunk(L):
+    return int(lib().dq_la_nchunk(int(L)))
+
+
+def gemm_last_error():
+    return int(lib().dq_gemm_last_error())

@@ -1,0 +1,447 @@
+"""Training harness — drop-in for /root/reference/dquartic/model/model_interface.py (ModelInterface 238-1150,
+WarmupLR_Scheduler 64-194, CallbackHandler 196-236) on B200.
+
+Kept from the reference: the public method names and arguments, epoch-level warm-up + half-cosine LR schedule,
+grad-clip 10.0 + AdamW(lr, betas (0.9, 0.999), eps 1e-8, weight_decay 0.01), checkpoint dictionary keys
+(`epoch, model_state_dict, optimizer_state_dict, scheduler_state_dict, best_loss`) and file naming, the
+0.5/0.5 mixing of the two drawn samples, `predict` returning dicts `{ms2_1, ms1_1, mixture, pred}`.
+
+New: the optimizer step is three fused kernels over the flat parameter buffer (`FusedAdamW`); a batch larger than
+`micro_batch` is processed by gradient accumulation; under `torch.distributed` the batch is sharded by sample and
+the flat gradient is all-reduced in buckets (the four 300 M-parameter mid-block buckets are launched as soon as the
+mid-stage backward has produced them, overlapping the long down-path backward); rank 0 writes checkpoints.
+Plotting / wandb tables (reference 669-976, 1152-1242) are out of scope.
+"""
+import functools
+import math
+import os
+from typing import List
+
+import numpy as np
+import torch
+from torch.optim.lr_scheduler import LambdaLR
+
+from .. import _native as N
+
+
+# ------------------------------------------------------------------------------------------------ LR schedule
+class LR_SchedulerInterface(object):
+    def __init__(self, optimizer, **kwargs):
+        raise NotImplementedError
+
+    def step(self, epoch: int, loss: float):
+        raise NotImplementedError
+
+    def get_last_lr(self) -> List[float]:
+        raise NotImplementedError
+
+
+def _warmup_cosine_lambda(current_step, *, num_warmup_steps, num_training_steps, num_cycles):
+    """reference model_interface.py:149-155."""
+    if current_step < num_warmup_steps:
+        return float(current_step + 1) / float(max(1, num_warmup_steps))
+    progress = float(current_step - num_warmup_steps) / float(max(1, num_training_steps - num_warmup_steps))
+    return max(1e-10, 0.5 * (1.0 + math.cos(math.pi * float(num_cycles) * 2.0 * progress)))
+
+
+class WarmupLR_Scheduler(LR_SchedulerInterface):
+    """Linear warm-up then half-cosine decay, stepped once per EPOCH (reference 64-194)."""
+
+    def __init__(self, optimizer, num_warmup_steps: int, num_training_steps: int, num_cycles: float = 0.5,
+                 last_epoch: int = -1, **kwargs):
+        self.optimizer = optimizer
+        self.lambda_lr = self.get_cosine_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps,
+                                                              num_cycles=num_cycles, last_epoch=last_epoch)
+
+    def step(self, epoch: int = None, loss=None):
+        return self.lambda_lr.step()
+
+    def get_last_lr(self) -> List[float]:
+        return self.lambda_lr.get_last_lr()
+
+    def _get_cosine_schedule_with_warmup_lr_lambda(self, current_step, *, num_warmup_steps, num_training_steps,
+                                                   num_cycles):
+        return _warmup_cosine_lambda(current_step, num_warmup_steps=num_warmup_steps,
+                                     num_training_steps=num_training_steps, num_cycles=num_cycles)
+
+    def get_cosine_schedule_with_warmup(self, optimizer, num_warmup_steps, num_training_steps, num_cycles=0.5,
+                                        last_epoch=-1):
+        fn = functools.partial(_warmup_cosine_lambda, num_warmup_steps=num_warmup_steps,
+                               num_training_steps=num_training_steps, num_cycles=num_cycles)
+        return LambdaLR(optimizer, fn, last_epoch)
+
+
+class CallbackHandler:
+    """No-op hooks; `epoch_callback` returning False stops training (reference 196-236)."""
+
+    def epoch_callback(self, epoch: int, epoch_loss: float) -> bool:
+        return True
+
+    def batch_callback(self, batch: int, batch_loss: float):
+        pass
+
+
+# ------------------------------------------------------------------------------------------------ optimizer
+class FusedAdamW(torch.optim.Optimizer):
+    """AdamW over the flat parameter buffer of a B200 `UNet1d`: grad-norm, clip coefficient and the update are
+    three kernels (dq_sumsq, dq_clip_coef, dq_adamw), no host synchronisation.  `state_dict()` /
+    `load_state_dict()` speak torch.optim.AdamW's per-parameter format so reference checkpoints round-trip."""
+
+    def __init__(self, net, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        self.net = net
+        params = list(net.parameters())
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False,
+                        foreach=None, capturable=False, differentiable=False, fused=None)
+        super().__init__(params, defaults)
+        self._m = None
+        self._v = None
+        self._step = 0
+        self._scratch = None
+        self.last_grad_norm = None
+
+    def _ensure_state(self):
+        flat = self.net.flat_params()
+        if self._m is None or self._m.device != flat.device:
+            self._m = torch.zeros_like(flat)
+            self._v = torch.zeros_like(flat)
+            self._sumsq = torch.zeros(1, dtype=torch.float64, device=flat.device)
+            self._coef = torch.zeros(2, dtype=torch.float32, device=flat.device)
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.net.zero_grad()
+
+    @torch.no_grad()
+    def step(self, closure=None, max_grad_norm=None):
+        self._ensure_state()
+        net = self.net
+        g = net.flat_grads()
+        p = net.flat_params()
+        n = net.n_trainable_flat
+        grp = self.param_groups[0]
+        lr, (b1, b2), eps, wd = grp["lr"], grp["betas"], grp["eps"], grp["weight_decay"]
+        self._step += 1
+        coef = None
+        if max_grad_norm is not None:
+            self._sumsq.zero_()
+            N.call("dq_sumsq", g, n, self._sumsq)
+            N.call("dq_clip_coef", self._sumsq, float(max_grad_norm), self._coef)
+            coef = self._coef
+            self.last_grad_norm = self._coef[0:1]
+        bc1 = 1.0 - b1 ** self._step
+        bc2 = 1.0 - b2 ** self._step
+        N.call("dq_adamw", p, g, self._m, self._v, n, coef, lr, b1, b2, eps, wd, lr / bc1, math.sqrt(bc2))
+        net.mark_params_modified()
+
+    # torch.optim.AdamW-compatible (de)serialisation -------------------------------------------------------
+    def state_dict(self):
+        self._ensure_state()
+        net = self.net
+        state = {}
+        names = list(net._params.keys())
+        for idx, name in enumerate(names):
+            if not net._params[name].requires_grad or self._step == 0:
+                continue
+            state[idx] = {"step": torch.tensor(float(self._step)),
+                          "exp_avg": net._view(self._m, name).clone(),
+                          "exp_avg_sq": net._view(self._v, name).clone()}
+        groups = [{k: v for k, v in self.param_groups[0].items() if k != "params"}]
+        groups[0]["params"] = list(range(len(names)))
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        self._ensure_state()
+        net = self.net
+        names = list(net._params.keys())
+        self._m.zero_()
+        self._v.zero_()
+        step = 0
+        for idx, st in sd["state"].items():
+            name = names[int(idx)]
+            net._view(self._m, name).copy_(st["exp_avg"])
+            net._view(self._v, name).copy_(st["exp_avg_sq"])
+            step = max(step, int(float(st["step"])))
+        self._step = step
+        for k, v in sd["param_groups"][0].items():
+            if k != "params":
+                self.param_groups[0][k] = v
+
+
+# ------------------------------------------------------------------------------------------------ harness
+class ModelInterface(object):
+    def __init__(self, device=None, min_pred_value: float = 0.0, **kwargs):
+        self.model: torch.nn.Module = None
+        self.optimizer = None
+        self.model_params: dict = {}
+        self.min_pred_value = min_pred_value
+        self.lr_scheduler_class = WarmupLR_Scheduler
+        self.callback_handler = CallbackHandler()
+        self.device = device if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.ms1_loss_weight = None
+        self.use_wandb = False
+        # B200 additions
+        self.micro_batch = None       # samples per forward/backward pass (None: whole batch)
+        self.max_grad_norm = 10.0     # reference model_interface.py:1121
+        self.grad_bucket_elems = 64 * 1024 * 1024
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__} with {self.model.__class__.__name__} model with "
+                f"{self.get_parameter_num()} parameters on {self.device}")
+
+    # ---------------------------------------------------------------------------------------- public
+    def build(self, model_class, **kwargs):
+        self.model = model_class  # an INSTANCE, as in the reference (model_interface.py:298-299)
+        self._init_for_training()
+
+    def get_parameter_num(self):
+        return np.sum([p.numel() for p in self.model.parameters()])
+
+    def train_step(self, x_0, ms2_cond=None, ms1_cond=None, noise=None, ms1_loss_weight=0.0):
+        raise NotImplementedError
+
+    def sample(self, x_t, ms2_cond=None, ms1_cond=None, num_steps=1000):
+        raise NotImplementedError
+
+    def _ckpt_latest(self, checkpoint_path):
+        return f"{os.path.dirname(checkpoint_path)}{os.path.sep}dquartic_latest_checkpoint.ckpt"
+
+    def _is_rank0(self):
+        return not (torch.distributed.is_available() and torch.distributed.is_initialized()) or \
+            torch.distributed.get_rank() == 0
+
+    def _run_epochs(self, dataloader, num_epochs, lr_scheduler, use_wandb, log_every_n_epochs, checkpoint_path):
+        start_epoch, best_loss, lr_scheduler = self.load_checkpoint(lr_scheduler, self._ckpt_latest(checkpoint_path),
+                                                                    self.device)
+        best_epoch = start_epoch
+        for epoch in range(start_epoch, num_epochs):
+            if hasattr(dataloader, "dataset") and hasattr(dataloader.dataset, "reset_epoch"):
+                dataloader.dataset.reset_epoch()
+            batch_loss = self._train_one_epoch(epoch, dataloader)
+            avg = float(np.mean(batch_loss))
+            if lr_scheduler is not None:
+                lr_scheduler.step(epoch, avg)
+                lr_now = lr_scheduler.get_last_lr()[0]
+            else:
+                lr_now = self.optimizer.param_groups[0]["lr"]
+            if use_wandb and self._is_rank0():
+                import wandb
+                wandb.log({"epoch": epoch, "train/loss": avg, "learning_rate": lr_now})
+            if self._is_rank0():
+                print(f"[Training] Epoch={epoch+1}, lr={lr_now}, loss={avg}")
+                self.save_checkpoint(lr_scheduler, epoch, avg, self._ckpt_latest(checkpoint_path))
+                if avg < best_loss:
+                    best_loss = avg
+                    best_epoch = epoch + 1
+                    self.save_checkpoint(lr_scheduler, epoch, best_loss, checkpoint_path)
+            elif avg < best_loss:
+                best_loss, best_epoch = avg, epoch + 1
+            if use_wandb and (epoch == 0 or epoch % log_every_n_epochs == 0) and self._is_rank0():
+                self.log_single_prediction(best_epoch, best_loss, dataloader, num_steps=[100, 500, 1000],
+                                           path=f"{os.path.dirname(checkpoint_path)}{os.path.sep}")
+            if not self.callback_handler.epoch_callback(epoch=epoch, epoch_loss=avg):
+                print(f"Training stopped at epoch {epoch}")
+                break
+        if self._is_rank0():
+            print(f"Best model checkpoint saved at epoch {best_epoch} with loss: {best_loss:.6f}")
+
+    def train_with_warmup(self, dataloader, num_epochs, num_warmup_steps=5, learning_rate=1e-4, use_wandb=True,
+                          log_every_n_epochs=100, checkpoint_path="best_model.ckpt"):
+        self._prepare_training(learning_rate)
+        lr_scheduler = self._get_lr_schedule_with_warmup(num_warmup_steps, num_epochs)
+        self.model.train()
+        self._run_epochs(dataloader, num_epochs, lr_scheduler, use_wandb, log_every_n_epochs, checkpoint_path)
+
+    def train(self, dataloader, batch_size, epochs, warmup_epochs: int = 5, learning_rate: float = 1e-4,
+              use_wandb: bool = False, checkpoint_path: str = "best_model.ckpt", **kwargs):
+        if self._is_rank0():
+            print(f"Info: Training {self!r}")
+        if warmup_epochs > 0:
+            self.train_with_warmup(dataloader, epochs, num_warmup_steps=warmup_epochs, learning_rate=learning_rate,
+                                   use_wandb=use_wandb, checkpoint_path=checkpoint_path, **kwargs)
+        else:
+            self._prepare_training(learning_rate, **kwargs)
+            self._run_epochs(dataloader, epochs, None, use_wandb, 100, checkpoint_path)
+
+    def load_checkpoint(self, scheduler, checkpoint_path, device):
+        if os.path.exists(checkpoint_path):
+            print(f"Loading checkpoint from {checkpoint_path}...")
+            checkpoint = torch.load(checkpoint_path, map_location=device, weights_only=False)
+            self.model.load_state_dict(checkpoint["model_state_dict"])
+            if self.optimizer is not None:
+                self.optimizer.load_state_dict(checkpoint["optimizer_state_dict"])
+            if scheduler is not None:
+                scheduler.lambda_lr.load_state_dict(checkpoint["scheduler_state_dict"])
+            epoch = checkpoint["epoch"]
+            best_loss = checkpoint["best_loss"]
+            print(f"Resumed from ({checkpoint_path}) epoch {epoch}, best loss {best_loss:.6f}")
+        else:
+            print(f"No checkpoint ({checkpoint_path}) found. Starting from scratch.")
+            epoch = 0
+            best_loss = float("inf")
+        return epoch, best_loss, scheduler
+
+    def save_checkpoint(self, scheduler, epoch, best_loss, checkpoint_path):
+        sd = {k: v.detach().contiguous().cpu() for k, v in self.model.state_dict().items()}
+        torch.save(
+            {
+                "epoch": epoch,
+                "model_state_dict": sd,
+                "optimizer_state_dict": self.optimizer.state_dict(),
+                "scheduler_state_dict": (scheduler.lambda_lr.state_dict() if scheduler is not None else None),
+                "best_loss": best_loss,
+            },
+            checkpoint_path,
+        )
+
+    def predict(self, dataloader, mixture_weights=(0.5, 0.5), num_steps=1000):
+        self.model.eval()
+        preds = np.array([])
+        for ms2_1, ms1_1, ms2_2, ms1_2 in dataloader:
+            x_0, ms1_cond, ms2_cond = self._mix_to_device(ms2_1, ms1_1, ms2_2, mixture_weights)
+            pred, _ = self._predict_one_batch(x_0, ms2_cond=ms2_cond, ms1_cond=ms1_cond, num_steps=num_steps)
+            preds = np.append(preds, {
+                "ms2_1": ms2_1.cpu().detach().numpy(),
+                "ms1_1": ms1_1.cpu().detach().numpy(),
+                "mixture": ms2_cond.cpu().detach().numpy(),
+                "pred": pred,
+            })
+        return preds
+
+    def log_single_prediction(self, *args, **kwargs):
+        try:
+            import pyopenms_viz  # noqa: F401
+        except ImportError:
+            raise ImportError("pyopenms_viz is required for plotting predictions (as in the reference); "
+                              "plotting is outside the B200 hot path")
+        raise NotImplementedError("plotting / wandb prediction tables are out of scope of the B200 build")
+
+    plot_single_prediction = log_single_prediction
+
+    # ---------------------------------------------------------------------------------------- private
+    def _init_for_training(self):
+        self.loss_func = torch.nn.L1Loss()
+
+    def _prepare_training(self, lr: float, **kwargs):
+        self.model.train()
+        self._set_lr(lr)
+
+    def _set_optimizer(self, lr):
+        if hasattr(self.model, "flat_params"):
+            self.optimizer = FusedAdamW(self.model, lr=lr)
+        else:  # an arbitrary user module (not the B200 denoiser): plain torch AdamW as in the reference
+            self.optimizer = torch.optim.AdamW(self.model.parameters(), lr=lr)
+
+    def _set_lr(self, lr: float):
+        if self.optimizer is None:
+            self._set_optimizer(lr)
+        else:
+            for g in self.optimizer.param_groups:
+                g["lr"] = lr
+
+    def _get_lr_schedule_with_warmup(self, warmup_epoch, epoch):
+        if warmup_epoch > epoch:
+            warmup_epoch = epoch // 2
+        return self.lr_scheduler_class(self.optimizer, num_warmup_steps=warmup_epoch, num_training_steps=epoch)
+
+    def _mix_to_device(self, ms2_1, ms1_1, ms2_2, mixture_weights):
+        """x_0 = ms2_1, ms1_cond = ms1_1, ms2_cond = w0*ms2_1 + w1*ms2_2 (reference 1071-1075), mixed on the GPU."""
+        dev = self.device
+        x_0 = ms2_1.to(dev, non_blocking=True).float().contiguous()
+        ms1_cond = ms1_1.to(dev, non_blocking=True).float().contiguous()
+        other = ms2_2.to(dev, non_blocking=True).float().contiguous()
+        if x_0.is_cuda:
+            ms2_cond = torch.empty_like(x_0)
+            N.call("dq_mix_affine", x_0, other, float(mixture_weights[0]), float(mixture_weights[1]), 1.0, 0.0,
+                   ms2_cond, x_0.numel())
+        else:
+            ms2_cond = x_0 * mixture_weights[0] + other * mixture_weights[1]
+        return x_0, ms1_cond, ms2_cond
+
+    def _train_one_epoch(self, epoch, dataloader, mixture_weights=(0.5, 0.5)):
+        self.model.train()
+        batch_loss = []
+        for batch_idx, (ms2_1, ms1_1, ms2_2, ms1_2) in enumerate(dataloader):
+            x_0, ms1_cond, ms2_cond = self._mix_to_device(ms2_1, ms1_1, ms2_2, mixture_weights)
+            loss = self._train_one_batch(x_0, ms2_cond=ms2_cond, ms1_cond=ms1_cond, noise=None,
+                                         ms1_loss_weight=self.ms1_loss_weight)
+            batch_loss.append(loss)
+            if self.use_wandb and self._is_rank0():
+                import wandb
+                wandb.log({"batch/train_loss": loss, "batch": batch_idx + epoch * len(dataloader)})
+        return batch_loss
+
+    def _allreduce_grads(self):
+        """Average the flat gradient over ranks in buckets (NCCL over NVLink; gloo in the CPU tests)."""
+        dist = torch.distributed
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        ws = dist.get_world_size()
+        if hasattr(self.model, "flat_grads"):
+            g = self.model.flat_grads()[: self.model.n_trainable_flat]
+            done = getattr(self, "_early_reduced", [])
+            works = []
+            pos = 0
+            ranges = []
+            for (o, n) in sorted(done):
+                if o > pos:
+                    ranges.append((pos, o - pos))
+                pos = o + n
+            if pos < g.numel():
+                ranges.append((pos, g.numel() - pos))
+            for (o, n) in ranges:
+                for s in range(o, o + n, self.grad_bucket_elems):
+                    e = min(o + n, s + self.grad_bucket_elems)
+                    works.append(dist.all_reduce(g[s:e], op=dist.ReduceOp.SUM, async_op=True))
+            for w in getattr(self, "_early_works", []) + works:
+                w.wait()
+            g.mul_(1.0 / ws)
+            self._early_reduced, self._early_works = [], []
+        else:
+            for p in self.model.parameters():
+                if p.grad is not None:
+                    dist.all_reduce(p.grad)
+                    p.grad.mul_(1.0 / ws)
+
+    def _train_one_batch(self, x_0, ms2_cond=None, ms1_cond=None, noise=None, ms1_loss_weight=0.0, t=None):
+        self.optimizer.zero_grad()
+        b = x_0.shape[0]
+        mb = b if not self.micro_batch else min(int(self.micro_batch), b)
+        total = None
+        n_mb = (b + mb - 1) // mb
+        for k, s in enumerate(range(0, b, mb)):
+            sl = slice(s, min(b, s + mb))
+            w = (sl.stop - sl.start) / b
+            kw = {} if t is None else {"t": t[sl]}
+            if hasattr(self.model, "_final_microbatch"):
+                self.model._final_microbatch = (k == n_mb - 1)
+            loss = self.train_step(
+                x_0[sl],
+                ms2_cond=None if ms2_cond is None else ms2_cond[sl],
+                ms1_cond=None if ms1_cond is None else ms1_cond[sl],
+                noise=None if noise is None else noise[sl],
+                ms1_loss_weight=ms1_loss_weight or 0.0,
+                **kw,
+            )
+            lm = loss.mean() * w
+            lm.backward()
+            total = lm.detach() if total is None else total + lm.detach()
+        self._allreduce_grads()
+        if isinstance(self.optimizer, FusedAdamW):
+            self.optimizer.step(max_grad_norm=self.max_grad_norm)
+        else:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.max_grad_norm)
+            self.optimizer.step()
+        self.last_loss = total
+        return total.item()
+
+    def _predict_one_batch(self, x_0, ms2_cond=None, ms1_cond=None, num_steps=1000):
+        self.model.eval()
+        with torch.no_grad():
+            sample, pred_noise = self.sample(torch.randn_like(x_0), ms2_cond=ms2_cond, ms1_cond=ms1_cond,
+                                             num_steps=num_steps)
+        return sample[0].cpu().detach().numpy(), pred_noise[0].cpu().detach().numpy()
+
+    def predict_batch(self, x_T, ms2_cond, ms1_cond, num_steps=50):
+        """Batched sampling that keeps every window (the reference drops all but item 0, 1150)."""
+        self.model.eval()
+        with torch.no_grad():
+            return self.sample(x_T, ms2_cond=ms2_cond, ms1_cond=ms1_cond, num_steps=num_steps)

@@ -1,0 +1,168 @@
+"""Dataset + synthetic multiplexing — drop-in for /root/reference/dquartic/utils/data_loader.py:10-185.
+
+`DIAMSDataset` keeps the reference's constructor, `__len__`, `__getitem__ -> 4 fp32 tensors`, `reset_epoch()`,
+the python-`random` pair rejection loop with per-epoch de-duplication (111-125; identical index sequence for an
+identical `random.seed`) and the per-pair min-max normalisation arithmetic (70-88, numpy semantics).
+
+`DeviceBatchLoader` is the B200 data path: the slice pool lives in HBM (or in pinned host memory, staged per
+batch), the host only draws the pair indices, and one fused kernel chain (csrc/data.cu) does min/max,
+normalisation and hands the four tensors to the harness on the device.  It is iterable like a DataLoader and
+exposes `.dataset`, so `ModelInterface.train(...)` accepts it unchanged.
+"""
+import os
+import random
+from typing import Literal
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from .. import _native as N
+
+
+class DIAMSDataset(Dataset):
+    def __init__(self, parquet_directory=None, ms2_file=None, ms1_file=None,
+                 normalize: Literal[None, "minmax"] = None):
+        if parquet_directory is None and ms1_file is not None and ms2_file is not None:
+            self.ms2_data = np.load(ms2_file, mmap_mode="r")
+            self.ms1_data = np.load(ms1_file, mmap_mode="r")
+            self.data_type = "npy"
+            print(f"Info: Loaded  {len(self.ms2_data)} MS2 slice samples and {len(self.ms1_data)} MS1 slice samples from NPY files.")
+        elif parquet_directory is not None and ms1_file is None and ms2_file is None:
+            self._load_parquet(parquet_directory)
+            self.data_type = "npy"  # staged into arrays once instead of two directory scans per item (reference 161-185)
+            print(f"Info: Loaded {len(self.ms2_data)} MS2 slice samples and MS1 slice samples from Parquet files.")
+        else:
+            raise ValueError(
+                "Invalid input data arguments. Please provide either a `parquet_directory` or `ms2_file` and `ms1_file`. "
+                f"Got parquet_directory={parquet_directory}, ms2_file={ms2_file}, ms1_file={ms1_file}.")
+        self.normalize = normalize
+        self.used_pairs = set()
+        self.epoch_reset = False
+
+    def _load_parquet(self, parquet_directory):
+        """pyarrow reader for the schema written by the reference's create_parquet_data
+        (utils/data_generation.py:206-223): ms1_data / ms2_data list<f32> + ms1_shape / ms2_shape."""
+        import glob
+        import pyarrow.parquet as pq
+
+        ms2, ms1 = [], []
+        for f in sorted(glob.glob(os.path.join(parquet_directory, "*.parquet"))):
+            tbl = pq.read_table(f, columns=["ms1_data", "ms2_data", "ms1_shape", "ms2_shape"]).to_pydict()
+            for a1, a2, s1, s2 in zip(tbl["ms1_data"], tbl["ms2_data"], tbl["ms1_shape"], tbl["ms2_shape"]):
+                ms2.append(np.asarray(a2, dtype=np.float32).reshape(tuple(s2)))
+                ms1.append(np.asarray(a1, dtype=np.float32).reshape(tuple(s1)))
+        if not ms2:
+            raise ValueError(f"no parquet slices found under {parquet_directory}")
+        self.ms2_data = np.stack(ms2)
+        self.ms1_data = np.stack(ms1)
+
+    def __len__(self):
+        return len(self.ms2_data)
+
+    def draw_pair(self):
+        """The reference's rejection loop (data_loader.py:111-125): returns (idx_1, idx_2)."""
+        n = len(self.ms2_data)
+        while True:
+            idx_1 = random.randint(0, n - 1)
+            idx_2 = random.randint(0, n - 1)
+            if idx_1 == idx_2:
+                continue
+            pair = tuple(sorted((idx_1, idx_2)))
+            if pair in self.used_pairs:
+                continue
+            self.used_pairs.add(pair)
+            return idx_1, idx_2
+
+    def __getitem__(self, idx):
+        i1, i2 = self.draw_pair()  # idx is ignored, as in the reference
+        a, a1, b, b1 = self.ms2_data[i1], self.ms1_data[i1], self.ms2_data[i2], self.ms1_data[i2]
+        if self.normalize == "minmax":
+            self.ms2_min = np.min([a.min(), b.min()])
+            self.ms2_max = np.max([a.max(), b.max()])
+            self.ms1_min = np.min([a1.min()])
+            self.ms1_max = np.max([a1.max()])
+            a = (a - self.ms2_min) / (self.ms2_max - self.ms2_min)
+            a1 = (a1 - self.ms1_min) / (self.ms1_max - self.ms1_min)
+            b = (b - self.ms2_min) / (self.ms2_max - self.ms2_min)
+            b1 = (b1 - self.ms1_min) / (self.ms1_max - self.ms1_min)
+        else:
+            raise ValueError("Invalid normalization method. Valid options are: None, 'minmax'.")
+        return tuple(torch.from_numpy(np.asarray(z).astype(np.float32)) for z in (a, a1, b, b1))
+
+    def reset_epoch(self):
+        self.used_pairs.clear()
+        self.epoch_reset = True
+
+
+class DeviceBatchLoader:
+    """GPU multiplexing loader.  pool='hbm': the whole pool is uploaded once; pool='pinned': the pool stays in
+    pinned host memory and only the drawn slices are copied per batch (async, on the current stream)."""
+
+    def __init__(self, dataset: DIAMSDataset, batch_size: int, device, pool: str = "hbm", batches_per_epoch=None,
+                 rank: int = 0, world_size: int = 1):
+        if dataset.normalize != "minmax":
+            raise ValueError("Invalid normalization method. Valid options are: None, 'minmax'.")
+        self.dataset = dataset
+        self.batch_size = int(batch_size)
+        self.device = torch.device(device)
+        self.pool = pool
+        n = len(dataset)
+        self.batches_per_epoch = batches_per_epoch or (n + self.batch_size - 1) // self.batch_size
+        ms2 = np.asarray(dataset.ms2_data)
+        ms1 = np.asarray(dataset.ms1_data)
+        if ms2.dtype in (np.int32, np.int64, np.int16, np.uint16, np.uint8, np.int8):
+            ms2, ms1, self.dtype_code = ms2.astype(np.int32), ms1.astype(np.int32), 0
+        else:
+            ms2, ms1, self.dtype_code = ms2.astype(np.float32), ms1.astype(np.float32), 1
+        self.rt, self.mz = ms2.shape[1], ms2.shape[2]
+        ms2_t, ms1_t = torch.from_numpy(np.ascontiguousarray(ms2)), torch.from_numpy(np.ascontiguousarray(ms1))
+        if pool == "hbm":
+            self.ms2 = ms2_t.to(self.device)
+            self.ms1 = ms1_t.to(self.device)
+        elif pool == "pinned":
+            self.ms2 = ms2_t.pin_memory()
+            self.ms1 = ms1_t.pin_memory()
+            self._stage2 = torch.empty((2 * self.batch_size, self.rt, self.mz), dtype=ms2_t.dtype).pin_memory()
+            self._stage1 = torch.empty((2 * self.batch_size, self.rt), dtype=ms1_t.dtype).pin_memory()
+        else:
+            raise ValueError("pool must be 'hbm' or 'pinned'")
+        self.h2d_bytes = 0
+
+    def __len__(self):
+        return self.batches_per_epoch
+
+    def draw(self, nb):
+        return [self.dataset.draw_pair() for _ in range(nb)]
+
+    def make_batch(self, pairs, want_cond=False, weights=(0.5, 0.5)):
+        nb = len(pairs)
+        dev = self.device
+        if self.pool == "hbm":
+            ms2, ms1 = self.ms2, self.ms1
+            pidx = torch.tensor(pairs, dtype=torch.long).to(dev, non_blocking=True)
+            self.h2d_bytes = pidx.numel() * 8
+        else:
+            flat = [i for p in pairs for i in p]
+            idx = torch.tensor(flat, dtype=torch.long)
+            torch.index_select(self.ms2, 0, idx, out=self._stage2[: 2 * nb])
+            torch.index_select(self.ms1, 0, idx, out=self._stage1[: 2 * nb])
+            ms2 = self._stage2[: 2 * nb].to(dev, non_blocking=True)
+            ms1 = self._stage1[: 2 * nb].to(dev, non_blocking=True)
+            pidx = torch.arange(2 * nb, dtype=torch.long).view(nb, 2).to(dev, non_blocking=True)
+            self.h2d_bytes = ms2.numel() * ms2.element_size() + ms1.numel() * ms1.element_size() + pidx.numel() * 8
+        x0 = torch.empty((nb, self.rt, self.mz), dtype=torch.float32, device=dev)
+        other = torch.empty_like(x0)
+        cond = torch.empty_like(x0) if want_cond else None
+        m1 = torch.empty((nb, self.rt), dtype=torch.float32, device=dev)
+        m2 = torch.empty_like(m1)
+        stats = torch.empty((nb, 4), dtype=torch.int32, device=dev)
+        N.call("dq_multiplex", ms2, ms1, self.dtype_code, pidx, stats, float(weights[0]), float(weights[1]), x0, other,
+               cond, m1, m2, nb, self.rt * self.mz, self.rt)
+        if want_cond:
+            return x0, m1, other, m2, cond
+        return x0, m1, other, m2
+
+    def __iter__(self):
+        for _ in range(self.batches_per_epoch):
+            yield self.make_batch(self.draw(self.batch_size))
