@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(128) block_bwd_kernel(BlockBwdArgs a) {
       part[2 * C + c] += d;                                    // d shift
       float dn = d * scale1[c];
       part[c] += dn * uh * sqrtC;                              // d g
-      float duh = dn * gl[c] * sqrtC;                          // d u-hat
+      float duh = a.g ? dn * gl[c] * sqrtC : dn;               // d u-hat (no norm: plain d u)
       dz[c] = duh;
       dot = fmaf(duh, uh, dot);
       uv[c] = uh;

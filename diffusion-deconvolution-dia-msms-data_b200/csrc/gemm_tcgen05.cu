@@ -4,7 +4,8 @@
 //
 // A and B are bf16, K-major (K contiguous).  The taps express the 3-tap Conv1d over the RT axis as an implicit
 // GEMM without im2col: tap t reads A shifted by a_row_off[t] rows and/or a_k_off[t] columns and B shifted by
-// b_k_off[t] columns, from slice b_tap[t] of a (taps, N, K) weight tensor.  Out-of-range coordinates are
+// b_k_off[t] columns (multiples of 8 elements: TMA needs a 16-byte aligned innermost coordinate), from slice
+// b_tap[t] of a (taps, N, K) weight tensor.  Out-of-range coordinates are
 // zero-filled by TMA, per-sample halo rows are physical zero rows in the padded activation layout
 // (see mid.cu), so no masking is needed in the main loop.
 //
@@ -31,7 +32,7 @@ struct GemmParams {
   long z_c_stride;
   int M, N, K, taps;
   int a_row_off[4], a_k_off[4], b_k_off[4], b_tap[4];
-  int z_b_koff_step;
+  int z_b_koff_step, z_b_tap_step;
   int accumulate;
   int m_tiles;
   unsigned long long* err;  // device flag set on pipeline timeout (bring-up safety)
@@ -163,7 +164,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
         const uint32_t sa = sbase + s * STAGE_BYTES, sb = sa + A_BYTES;
         tma_load_2d(sa, &tmA, full0 + 8 * s, kb * BK + p.a_k_off[tap], m0 + p.a_row_off[tap]);
-        tma_load_3d(sb, &tmB, full0 + 8 * s, kb * BK + p.b_k_off[tap] + z * p.z_b_koff_step, n0, p.b_tap[tap]);
+        tma_load_3d(sb, &tmB, full0 + 8 * s, kb * BK + p.b_k_off[tap] + z * p.z_b_koff_step, n0, p.b_tap[tap] + z * p.z_b_tap_step);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -277,7 +278,7 @@ using namespace dq;
 DQ_API int dq_gemm_bf16_tn(const void* A, long a_rows, long a_cols, long a_ld, const void* B, long b_rows, long b_cols,
                            long b_ld, long b_tap_stride, int b_ntaps, float* C, long ldc, const float* bias,
                            int accumulate, int M, int N, int K, int taps, const int* offs, int nz, int z_b_koff_step,
-                           long z_c_stride, int bn, void* stream) {
+                           int z_b_tap_step, long z_c_stride, int bn, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (taps < 1 || taps > 4) return -2;
   if ((a_ld % 8) || (b_ld % 8) || (b_tap_stride % 8) || (((size_t)A) & 15) || (((size_t)B) & 15)) return -4;
@@ -315,7 +316,9 @@ DQ_API int dq_gemm_bf16_tn(const void* A, long a_rows, long a_cols, long a_ld, c
   for (int i = 0; i < 4; ++i) {
     p.a_row_off[i] = offs[i]; p.a_k_off[i] = offs[4 + i]; p.b_k_off[i] = offs[8 + i]; p.b_tap[i] = offs[12 + i];
   }
-  p.z_b_koff_step = z_b_koff_step; p.accumulate = accumulate; p.m_tiles = (M + BM - 1) / BM; p.err = g_err_flag;
+  for (int i = 0; i < taps; ++i) if ((offs[4 + i] % 8) || (offs[8 + i] % 8)) return -4;
+  if (z_b_koff_step % 8) return -4;
+  p.z_b_koff_step = z_b_koff_step; p.z_b_tap_step = z_b_tap_step; p.accumulate = accumulate; p.m_tiles = (M + BM - 1) / BM; p.err = g_err_flag;
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 256) return launch_gemm<256, 4>(tmA, tmB, p, nz < 1 ? 1 : nz, st);
   return launch_gemm<128, 6>(tmA, tmB, p, nz < 1 ? 1 : nz, st);

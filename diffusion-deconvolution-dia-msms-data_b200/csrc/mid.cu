@@ -32,13 +32,15 @@ __global__ void __launch_bounds__(256) mid_pack_kernel(const float* __restrict__
 
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in,
                                                              __nv_bfloat16* __restrict__ out, int rows, int cols,
-                                                             long ld_out) {
+                                                             long ld_out, int row_shift) {
+  // out[c][r] = in[r + row_shift][c] (zero outside): the tap shift of the RT convolution is applied here
+  // because TMA cannot start a box at an odd element of the contiguous dimension.
   __shared__ __nv_bfloat16 tile[32][34];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int i = ty; i < 32; i += 8) {
-    int r = r0 + i, c = c0 + tx;
-    tile[i][tx] = (r < rows && c < cols) ? in[(size_t)r * cols + c] : __float2bfloat16(0.f);
+    int r = r0 + i + row_shift, c = c0 + tx;
+    tile[i][tx] = (r >= 0 && r < rows && c < cols) ? in[(size_t)r * cols + c] : __float2bfloat16(0.f);
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
@@ -379,10 +381,10 @@ DQ_API int dq_mid_pack(const float* x, void* out_bf16, int b, int rt, int N, int
   DQ_LAUNCH_CHECK();
   return 0;
 }
-DQ_API int dq_transpose_bf16(const void* in, void* out, int rows, int cols, long ld_out, void* stream) {
+DQ_API int dq_transpose_bf16(const void* in, void* out, int rows, int cols, long ld_out, int row_shift, void* stream) {
   if (rows <= 0 || cols <= 0) return 0;
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
-  transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, rows, cols, ld_out);
+  transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, rows, cols, ld_out, row_shift);
   DQ_LAUNCH_CHECK();
   return 0;
 }

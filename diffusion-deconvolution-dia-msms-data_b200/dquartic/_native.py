@@ -34,9 +34,9 @@ _SIGS = {
     "dq_act_fwd": ("ppils", 1),
     "dq_act_bwd": ("pppils", 1),
     "dq_ncl_nlc": ("ppiiiis", 1),
-    "dq_gemm_bf16_tn": ("plllplllliplpiiiiihiilis", 1),
+    "dq_gemm_bf16_tn": ("plllplllliplpiiiiihiiilis", 1),
     "dq_mid_pack": ("ppiiiis", 1),
-    "dq_transpose_bf16": ("ppiils", 1),
+    "dq_transpose_bf16": ("ppiilis", 1),
     "dq_cast_transpose": ("pppiis", 1),
     "dq_rownorm_fwd": ("pippiipppipiiis", 1),
     "dq_rownorm_bwd": ("pipippiipppipipppiiis", 2),

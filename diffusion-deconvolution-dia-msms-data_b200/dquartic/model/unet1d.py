@@ -140,8 +140,10 @@ class UNet1d(nn.Module):
         downsample_dim=40000,
         simple=True,
         pos_output_only=False,
+        device=None,
     ):
         super().__init__()
+        self._init_device = device  # B200 addition: build the flat buffer directly on this device
         # The reference's other branches are dead code (SURVEY.md findings 2, §2 "OUT OF SCOPE" rows): refuse loudly.
         if not simple:
             raise NotImplementedError("simple=False crashes in the reference (unet1d.py:822); only simple=True is built")
@@ -237,7 +239,7 @@ class UNet1d(nn.Module):
         return v.view(shape)
 
     def _register(self):
-        self._flat = torch.zeros(self.n_flat, dtype=torch.float32)
+        self._flat = torch.zeros(self.n_flat, dtype=torch.float32, device=self._init_device)
         self._params = OrderedDict()
         for name in self.specs:
             parts = name.split(".")
@@ -475,11 +477,11 @@ class UNet1d(nn.Module):
 
     # ---- GEMM wrappers -------------------------------------------------------------------------------------
     def _gemm(self, A, a_rows, a_cols, a_ld, B, b_rows, b_cols, b_ld, b_tap_stride, b_ntaps, C, ldc, bias, acc, M, Nn,
-              K, taps, a_row_off, a_k_off, b_k_off, b_tap, nz=1, z_b_koff_step=0, z_c_stride=0):
+              K, taps, a_row_off, a_k_off, b_k_off, b_tap, nz=1, z_b_koff_step=0, z_c_stride=0, z_b_tap_step=0):
         offs = list(a_row_off) + [0] * (4 - len(a_row_off)) + list(a_k_off) + [0] * (4 - len(a_k_off)) \
             + list(b_k_off) + [0] * (4 - len(b_k_off)) + list(b_tap) + [0] * (4 - len(b_tap))
         N.call("dq_gemm_bf16_tn", A, a_rows, a_cols, a_ld, B, b_rows, b_cols, b_ld, b_tap_stride, b_ntaps, C, ldc,
-               bias, acc, M, Nn, K, taps, offs, nz, z_b_koff_step, z_c_stride, self.gemm_bn)
+               bias, acc, M, Nn, K, taps, offs, nz, z_b_koff_step, z_b_tap_step, z_c_stride, self.gemm_bn)
 
     gemm_bn = 128
 
@@ -508,11 +510,12 @@ class UNet1d(nn.Module):
         Mp = b * (rt + 2)
         ld = _ceil8(Mp)
         dUT = self._empty(Nm, ld, dtype=torch.bfloat16)
-        AT = self._empty(Nm, ld, dtype=torch.bfloat16)
-        N.call("dq_transpose_bf16", dUp, dUT, Mp, Nm, ld)
-        N.call("dq_transpose_bf16", Ap, AT, Mp, Nm, ld)
-        self._gemm(dUT, Nm, Mp, ld, AT, Nm, Mp, ld, 0, 1, self._gw(wname), Nm, None, 1, Nm, Nm, Mp, 1,
-                   (0,), (0,), (-1,), (0,), nz=3, z_b_koff_step=1, z_c_stride=Nm * Nm)
+        AT3 = self._empty(3, Nm, ld, dtype=torch.bfloat16)  # AT3[t][ci][m'] = A[m' + t - 1][ci]
+        N.call("dq_transpose_bf16", dUp, dUT, Mp, Nm, ld, 0)
+        for t in range(3):
+            N.call("dq_transpose_bf16", Ap, AT3[t], Mp, Nm, ld, t - 1)
+        self._gemm(dUT, Nm, Mp, ld, AT3, Nm, Mp, ld, Nm * ld, 3, self._gw(wname), Nm, None, 1, Nm, Nm, Mp, 1,
+                   (0,), (0,), (0,), (0,), nz=3, z_b_tap_step=1, z_c_stride=Nm * Nm)
 
     def _mid_block_fwd(self, pre, X, b, rt, save):
         """X fp32 [M][N] -> fp32 [M][N]; ResnetBlock(N, N) with identity skip (unet1d.py:1029/1058)."""
@@ -588,8 +591,8 @@ class UNet1d(nn.Module):
         # d to_out weight [N][128] += dOut^T . O
         dOT = self._empty(Nm, ld, dtype=torch.bfloat16)
         OT = self._empty(HD, ld, dtype=torch.bfloat16)
-        N.call("dq_transpose_bf16", dOb, dOT, M, Nm, ld)
-        N.call("dq_transpose_bf16", O, OT, M, HD, ld)
+        N.call("dq_transpose_bf16", dOb, dOT, M, Nm, ld, 0)
+        N.call("dq_transpose_bf16", O, OT, M, HD, ld, 0)
         self._gemm(dOT, Nm, M, ld, OT, HD, M, ld, 0, 1, self._gw("mid_attn.fn.fn.to_out.weight"), HD, None, 1, Nm, HD,
                    M, 1, (0,), (0,), (0,), (0,))
         # d O = dOut . Wout
@@ -607,8 +610,8 @@ class UNet1d(nn.Module):
         # d Wqv [256][N] += dqv^T . xn
         dqvT = self._empty(2 * HD, ld, dtype=torch.bfloat16)
         xnT = self._empty(Nm, ld, dtype=torch.bfloat16)
-        N.call("dq_transpose_bf16", dqvb, dqvT, M, 2 * HD, ld)
-        N.call("dq_transpose_bf16", xn, xnT, M, Nm, ld)
+        N.call("dq_transpose_bf16", dqvb, dqvT, M, 2 * HD, ld, 0)
+        N.call("dq_transpose_bf16", xn, xnT, M, Nm, ld, 0)
         self._gemm(dqvT, 2 * HD, M, ld, xnT, Nm, M, ld, 0, 1, self._gw("mid_attn.fn.fn.to_qv.weight"), Nm, None, 1,
                    2 * HD, Nm, M, 1, (0,), (0,), (0,), (0,))
         # d xn = dqv . Wqv

@@ -80,11 +80,11 @@ int dq_ncl_nlc(const float* in, float* out, int B, int C, int L, int reverse, vo
 /* tcgen05/TMEM/TMA multi-tap GEMM: C[M,N] (+)= sum_tap A_tap[M,K] . B_tap[N,K]^T (+bias); A, B bf16 K-major. */
 int dq_gemm_bf16_tn(const void* A, long a_rows, long a_cols, long a_ld, const void* B, long b_rows, long b_cols,
                     long b_ld, long b_tap_stride, int b_ntaps, float* C, long ldc, const float* bias, int accumulate,
-                    int M, int N, int K, int taps, const int* offs, int nz, int z_b_koff_step, long z_c_stride,
-                    int bn, void* stream);
+                    int M, int N, int K, int taps, const int* offs, int nz, int z_b_koff_step, int z_b_tap_step,
+                    long z_c_stride, int bn, void* stream);
 int dq_gemm_last_error(void);
 int dq_mid_pack(const float* x, void* out_bf16, int b, int rt, int N, int pad, void* stream);
-int dq_transpose_bf16(const void* in, void* out, int rows, int cols, long ld_out, void* stream);
+int dq_transpose_bf16(const void* in, void* out, int rows, int cols, long ld_out, int row_shift, void* stream);
 int dq_cast_transpose(const float* in, void* out_bf16, void* out_t_bf16, int rows, int cols, void* stream);
 int dq_rownorm_fwd(const float* u, int upad, const float* g, const float* ss, int ss_stride, int act, const float* res,
                    float* out_f32, void* out_bf16, int opad, float* inv_out, int b, int rt, int N, void* stream);
