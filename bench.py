@@ -1,0 +1,392 @@
+"""bench.py — headline benchmark of the B200-native dquartic hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): default denoiser (1,204,738,391 parameters, dquartic_train_config.json),
+bf16 tensor-core mid stage / fp32 elsewhere, synthetic multiplexed MS2 maps of the config's shape
+(34 x 40000), batch 256 per GPU.  A "step" is one optimizer step over one batch: multiplexing of 256 drawn pairs,
+q_sample, U-Net forward/backward (gradient accumulation over micro-batches), epsilon-MSE, grad-clip 10 + AdamW.
+N > 1 (torchrun): weak scaling, 256 samples per GPU, one bucketed NCCL gradient all-reduce per step.
+
+One JSON line on rank 0:
+  value      train samples/s, inputs resident in HBM (pool in HBM, pair indices pre-uploaded)
+  e2e        the same through the public API with HOST buffers: pool in pinned host memory, per-step H2D copy of
+             the drawn raw slices, loss read back to the host every step
+  roofline   dominant kernel (measured live with CUDA events), see DESIGN.md
+  cpu_baseline  the oracle port (torch fp32 CPU restatement of the reference) on the host cores, bounded sample
+  sampling   DDIM-sampled MS2 maps/s (50 steps), extra to the contract
+`--impl reference` times the reference's CPU implementation of the same step (the oracle port: the reference is
+pure Python and /root/reference does not exist on the GPU box), one sample per step.
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "diffusion-deconvolution-dia-msms-data_b200"))
+
+DEFAULT_CFG = dict(dim=4, channels=1, dim_mults=[1, 2, 2, 3, 3, 4, 4], conditional=True, init_cond_channels=1,
+                   attn_cond_channels=1, tfer_dim_mult=620, downsample_dim=40000, simple=True)
+RT, MZ = 34, 40000
+FWD_GFLOP_PER_SAMPLE = 212.87  # SURVEY.md §8d (FlopCounterMode on the reference at b = 1)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the training step (oracle port), one sample per step."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import dquartic_oracle as O
+
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    v, sample = cpu_train_step_rate(O, torch, steps=args.steps, warmup=args.warmup)
+    ms = 1000.0 / v
+    line = {
+        "impl": "reference", "metric": "train_samples_per_s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(1, 1, per_gpu_batch=1),
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_train_step_rate(O, torch, steps, warmup):
+    """fwd + bwd + clip + AdamW of ONE full-size sample per step on the CPU (batched oracle at b = 1)."""
+    cfg = DEFAULT_CFG
+    P = {}
+    g = torch.Generator().manual_seed(0)
+    for name, shape in O.param_shapes(cfg).items():
+        if name.endswith("freqs"):
+            P[name] = O.rotary_freqs()
+            continue
+        fan_in = 1
+        for s in shape[1:]:
+            fan_in *= s
+        if name.endswith(".g"):
+            P[name] = torch.ones(shape)
+        else:
+            P[name] = (torch.rand(shape, generator=g) * 2 - 1) / max(1.0, fan_in) ** 0.5
+        P[name].requires_grad_(True)
+    _, _, ab = O.schedule_tables(1000, "cosine")
+    names = [k for k in P if P[k].requires_grad]
+    m = {k: torch.zeros_like(P[k]) for k in names}
+    v = {k: torch.zeros_like(P[k]) for k in names}
+    x0 = torch.rand(1, RT, MZ, generator=g) * (torch.rand(1, RT, MZ, generator=g) < 0.02)
+    other = torch.rand(1, RT, MZ, generator=g) * (torch.rand(1, RT, MZ, generator=g) < 0.02)
+    cond = O.mix(x0, other)
+    ms1 = torch.rand(1, RT, generator=g)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        t = torch.randint(0, 1000, (1,), generator=g)
+        noise = torch.randn(1, RT, MZ, generator=g)
+        for k in names:
+            P[k].grad = None
+        loss, _ = O.train_loss(P, cfg, ab, x0, cond, ms1, t, noise)
+        loss.backward()
+        with torch.no_grad():
+            grads, _ = O.clip_grad_norm([P[k].grad for k in names])
+            for k, gk in zip(names, grads):
+                p_new, m[k], v[k] = O.adamw_step(P[k], gk, m[k], v[k], it + 1, 1e-5)
+                P[k].copy_(p_new)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return 1.0 / mean, f"{len(times)} optimizer step(s) at batch 1 (fwd+bwd+clip+AdamW), full-size model, fp32, {mean:.1f} s/step"
+
+
+def workload_config(world, micro_batch, per_gpu_batch):
+    return {
+        "workload": "configs[1]: default DDIM denoiser (1,204,738,391 params), synthetic multiplexed MS2 34x40000, "
+                    f"batch {per_gpu_batch}/GPU, one optimizer step per bench step",
+        "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * world, "micro_batch": micro_batch,
+        "rt": RT, "mz": MZ, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (activations >> 126 MB per step)",
+    }
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--batch", type=int, default=256, help="samples per GPU per optimizer step")
+    ap.add_argument("--micro-batch", type=int, default=32)
+    ap.add_argument("--pool", type=int, default=96, help="synthetic pool size (slices)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sampling", action="store_true")
+    ap.add_argument("--sample-windows", type=int, default=8)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from dquartic import _native as N
+    from dquartic.model.model import DDIMDiffusionModel
+    from dquartic.model.unet1d import UNet1d
+    from dquartic.utils.data_loader import DeviceBatchLoader, DIAMSDataset
+    from dquartic.utils.synthetic import synth_pool
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+
+    # ---- synthetic pool (same on every rank), written to npy so the public DIAMSDataset path is used
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix=f"dq_bench_{rank}_")
+    ms2, ms1 = synth_pool(args.pool, RT, MZ, seed=1234)
+    np.save(os.path.join(tmp, "ms2.npy"), ms2)
+    np.save(os.path.join(tmp, "ms1.npy"), ms1)
+    ds = DIAMSDataset(ms2_file=os.path.join(tmp, "ms2.npy"), ms1_file=os.path.join(tmp, "ms1.npy"), normalize="minmax")
+    random.seed(1234 + rank)
+    torch.manual_seed(1234 + rank)
+
+    # ---- model (random init of the default architecture, identical on every rank)
+    cfg = DEFAULT_CFG
+    gen_state = torch.random.get_rng_state()
+    torch.manual_seed(1234)
+    net = UNet1d(dim=cfg["dim"], channels=1, dim_mults=tuple(cfg["dim_mults"]), conditional=True, init_cond_channels=1,
+                 attn_cond_channels=1, downsample_dim=cfg["downsample_dim"], simple=True, device=dev)
+    torch.random.set_rng_state(gen_state)
+    if world > 1:
+        dist.broadcast(net.flat_params(), src=0)
+        net.mark_params_modified()
+    ddim = DDIMDiffusionModel(net, device=dev)
+    ddim.micro_batch = args.micro_batch
+    ddim._prepare_training(1e-5)
+    B = args.batch
+
+    hbm_loader = DeviceBatchLoader(ds, B, dev, pool="hbm")
+    pin_loader = DeviceBatchLoader(ds, B, dev, pool="pinned")
+
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def draw(loader):
+        ds.reset_epoch()
+        return loader.draw(B)
+
+    # ---- value: inputs resident in HBM when the timed region starts
+    def run_loop(n_warm, n_timed, e2e):
+        loader = pin_loader if e2e else hbm_loader
+        batches = None
+        if not e2e:
+            batches = [loader.make_batch(draw(loader), want_cond=True) for _ in range(min(2, n_warm + n_timed))]
+        for i in range(n_warm):
+            if e2e:
+                x0, m1, other, m2 = loader.make_batch(draw(loader))
+                x0, m1c, cond = ddim._mix_to_device(x0, m1, other, (0.5, 0.5))
+                ddim._train_one_batch(x0, cond, m1c)
+            else:
+                x0, m1, other, m2, cond = batches[i % len(batches)]
+                ddim._train_one_batch(x0, cond, m1)
+        barrier()
+        l0 = N.launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(n_timed):
+            if e2e:
+                x0, m1, other, m2 = loader.make_batch(draw(loader))
+                x0, m1c, cond = ddim._mix_to_device(x0, m1, other, (0.5, 0.5))
+                ddim._train_one_batch(x0, cond, m1c)  # returns loss.item(): device -> host read every step
+            else:
+                x0, m1, other, m2, cond = batches[i % len(batches)]
+                ddim._train_one_batch(x0, cond, m1)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, N.launches - l0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches = run_loop(args.warmup, args.steps, e2e=False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step / 1000.0)
+
+    ms_e2e_total, _ = run_loop(1, args.steps, e2e=True)
+    ms_e2e = ms_e2e_total / args.steps
+    e2e_value = B * world / (ms_e2e / 1000.0)
+    h2d = pin_loader.h2d_bytes
+    d2h = 4
+
+    extra = {}
+    if rank == 0:
+        extra["roofline"] = dominant_kernel_roofline(torch, N, net, dev)
+        extra["step_breakdown"] = {"train_gflop_per_sample": 3 * FWD_GFLOP_PER_SAMPLE,
+                                   "achieved_tflops_whole_step": 3 * FWD_GFLOP_PER_SAMPLE * B / ms_step,
+                                   "frac_of_bf16_sustained_peak": 3 * FWD_GFLOP_PER_SAMPLE * B / ms_step / peaks()["tensor_sustained"]}
+    if not args.no_sampling:
+        extra_s = sampling_rate(torch, dist, ddim, hbm_loader, ds, dev, world, args.sample_windows)
+        if rank == 0:
+            extra["sampling"] = extra_s
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import dquartic_oracle as O
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        v, sample = cpu_train_step_rate(O, torch, steps=1, warmup=0)
+        extra["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 (mid-stage tcgen05 GEMMs, fp32 accumulate) / f32 elsewhere",
+            "data": "synthetic", "config": workload_config(world, args.micro_batch, B),
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(torch, N, net, dev):
+    """Times the linear-attention backward (the kernel family that dominates the step, see profiles/) at level 0
+    (C = 4, L = 40000, 32 samples) alone with CUDA events on the launch stream.  Algorithmic work per launch
+    (DESIGN.md): forward contractions are 557056 x L FLOP per level per SAMPLE; backward = 2.5 x."""
+    n_samples = 32
+    R, C, L = n_samples * RT, 4, MZ
+    pre = "downs.0.2"
+    x = torch.randn(R, C, L, device=dev)
+    dres = torch.randn(R, C, L, device=dev)
+    net._ensure_grads()
+    out, saved = net._la_fwd(pre, x, True)
+    for _ in range(2):
+        net._la_bwd(pre, saved, dres)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    ev0.record()
+    for _ in range(reps):
+        net._la_bwd(pre, saved, dres)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / reps
+    flops = 2.5 * 557056.0 * L * n_samples
+    achieved = flops / (ms * 1e-3) / 1e12
+    pk = peaks()
+    net._gflat.zero_()
+    return {"kernel": "dq_linattn_bwd (la_bwd_q + la_bwd_combine + la_bwd_kv), level 0, 32 samples",
+            "bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
+            "traffic": None, "ms_per_launch": ms, "peak_source": pk["src"],
+            "note": "fp32 CUDA-core implementation in round 1: measured against the dense bf16 tensor peak it will move to"}
+
+
+def sampling_rate(torch, dist, ddim, loader, ds, dev, world, windows):
+    """DDIM sampling (50 steps) of `windows` windows per GPU, sharded by window, no collective."""
+    ds.reset_epoch()
+    x0, m1, other, m2, cond = loader.make_batch(loader.draw(windows), want_cond=True)
+    xT = torch.randn_like(x0)
+    ddim.model.eval()
+    with torch.no_grad():
+        ddim.sample(xT, cond, m1, num_steps=2)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        ddim.sample(xT, cond, m1, num_steps=50)
+        ev1.record()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    ddim.model.train()
+    return {"metric": "ddim_maps_per_s", "value": windows * world / (ms / 1000.0), "unit": "maps/s", "num_steps": 50,
+            "windows_per_gpu": windows, "ms_total": ms}
+
+
+if __name__ == "__main__":
+    main()

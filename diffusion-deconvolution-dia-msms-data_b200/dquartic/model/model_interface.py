@@ -369,6 +369,23 @@ class ModelInterface(object):
                 wandb.log({"batch/train_loss": loss, "batch": batch_idx + epoch * len(dataloader)})
         return batch_loss
 
+    def _dist_on(self):
+        dist = torch.distributed
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _early_allreduce(self, ranges):
+        """Called from the denoiser's backward as soon as the mid-stage gradients are final: start their
+        all-reduce (async, NCCL stream) so it overlaps the down-path backward."""
+        dist = torch.distributed
+        g = self.model.flat_grads()
+        self._early_reduced = list(getattr(self, "_early_reduced", []))
+        self._early_works = list(getattr(self, "_early_works", []))
+        for (o, n) in ranges:
+            for s in range(o, o + n, self.grad_bucket_elems):
+                e = min(o + n, s + self.grad_bucket_elems)
+                self._early_works.append(dist.all_reduce(g[s:e], op=dist.ReduceOp.SUM, async_op=True))
+            self._early_reduced.append((o, n))
+
     def _allreduce_grads(self):
         """Average the flat gradient over ranks in buckets (NCCL over NVLink; gloo in the CPU tests)."""
         dist = torch.distributed
@@ -403,6 +420,8 @@ class ModelInterface(object):
 
     def _train_one_batch(self, x_0, ms2_cond=None, ms1_cond=None, noise=None, ms1_loss_weight=0.0, t=None):
         self.optimizer.zero_grad()
+        if hasattr(self.model, "grad_ready_callback"):
+            self.model.grad_ready_callback = self._early_allreduce if self._dist_on() else None
         b = x_0.shape[0]
         mb = b if not self.micro_batch else min(int(self.micro_batch), b)
         total = None

@@ -183,6 +183,10 @@ class UNet1d(nn.Module):
         self._bf16_version = -1
         self._manual_version = 0
         self.last_tape = None
+        # data-parallel hook: called from backward with [(flat offset, numel)] of gradients that are final
+        # (the four 300 M mid-conv weights + mid attention projections) while the down-path backward still runs
+        self.grad_ready_callback = None
+        self._final_microbatch = True
 
     # ---------------------------------------------------------------------------------------------- layout
     def _ss_producers(self):
@@ -329,6 +333,11 @@ class UNet1d(nn.Module):
             for name, par in self._params.items():
                 if par.requires_grad and par.grad is None:
                     par.grad = self._view(self._gflat, name)
+
+    def early_grad_ranges(self):
+        names = [f"mid_block{i}.block{j}.proj.weight" for i in (1, 2) for j in (1, 2)]
+        names += ["mid_attn.fn.fn.to_qv.weight", "mid_attn.fn.fn.to_out.weight"]
+        return [(self.offsets[n], int(np.prod(self.specs[n]))) for n in names]
 
     def _w(self, name):
         """Contiguous flat slice of a parameter (memory order; mid convs are [3][co][ci])."""
@@ -784,6 +793,8 @@ class UNet1d(nn.Module):
         dm, dcond = self._mid_attn_bwd(S["sma"], dm, b, rt)
         dm = self._mid_block_bwd("mid_block1", S["sm1"], dm, b, rt)
         dcur = dm.view(R, d, mzd)
+        if self.grad_ready_callback is not None and self._final_microbatch:
+            self.grad_ready_callback(self.early_grad_ranges())
 
         # up level j popped the skips of down level (n_lv-1-j); skip_grads was appended for j = n_lv-1 .. 0
         sg = {}

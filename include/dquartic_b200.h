@@ -99,7 +99,7 @@ int dq_attn_core_bwd(const float* qv, const float* k, const float* freqs, const 
 
 /* ---- optimizer (model/model_interface.py:1011, 1121-1122) --------------------------------------------- */
 int dq_sumsq(const float* x, long n, double* out, void* stream);
-int dq_clip_coef(const double* sumsq, float max_norm, float* out /* [norm, coef] */, void* stream);
+int dq_clip_coef(const double* sumsq, float max_norm, float* out_norm_coef, void* stream);
 int dq_adamw(float* p, const float* g, float* m, float* v, long n, const float* coef_ptr, float lr, float b1, float b2,
              float eps, float wd, float step_size, float bc2_sqrt, void* stream);
 int dq_fill(float* p, float v, long n, void* stream);
