@@ -279,7 +279,7 @@ struct ConvBwdWeightArgs {
   const float* in_ss;  // source-1 affine as in forward (or null)
   float* dw;         // (cout, cin, K) accumulated (atomic)
   float* db;         // (cout) accumulated (atomic) or null
-  int c1, c2, cout, R, Lin, Lout, pad, rows_per_block, rows_per_sample, in_ss_stride;
+  int c1, c2, cout, R, Lin, Lout, pad, rows_per_block, rows_per_sample, in_ss_stride, strip, strips;
 };
 
 template <int K, int STRIDE, int UP>
@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(ConvBwdWeightArgs 
   __shared__ float red[4 * NV];
   const int cin = a.c1 + a.c2;
   const int co0 = blockIdx.y * T, ci0 = blockIdx.z * T;
-  const int r0 = blockIdx.x * a.rows_per_block, r1 = min(a.R, r0 + a.rows_per_block);
+  const int r0 = (blockIdx.x / a.strips) * a.rows_per_block, r1 = min(a.R, r0 + a.rows_per_block);
+  const int lo0 = (blockIdx.x % a.strips) * a.strip, lo1 = min(a.Lout, lo0 + a.strip);
   const int LinV = a.Lin * UP;
   float acc[NV];
 #pragma unroll
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(ConvBwdWeightArgs 
         }
       } else xr[t] = a.x2 + ((size_t)r * a.c2 + (ci - a.c1)) * a.Lin;
     }
-    for (int lo = threadIdx.x; lo < a.Lout; lo += blockDim.x) {
+    for (int lo = lo0 + threadIdx.x; lo < lo1; lo += blockDim.x) {
       float d[T];
 #pragma unroll
       for (int t = 0; t < T; ++t) {
@@ -403,10 +404,13 @@ static int launch_bwd_data(const ConvBwdDataArgs& a, cudaStream_t st) {
 template <int K, int STRIDE, int UP>
 static int launch_bwd_weight(ConvBwdWeightArgs a, cudaStream_t st) {
   int cin = a.c1 + a.c2;
-  // ~8192 positions per block so the block-level reduction is amortised
-  int rpb = max(1, 8192 / max(1, a.Lout));
+  // ~4096 positions per block: enough work to amortise the block-level reduction, enough blocks to fill 148 SMs
+  constexpr int kStrip = 4096;
+  int rpb = max(1, kStrip / max(1, a.Lout));
   a.rows_per_block = rpb;
-  dim3 grid((unsigned)((a.R + rpb - 1) / rpb), (unsigned)((a.cout + 3) / 4), (unsigned)((cin + 3) / 4));
+  a.strip = (a.Lout > kStrip) ? kStrip : a.Lout;
+  a.strips = (a.Lout + a.strip - 1) / a.strip;
+  dim3 grid((unsigned)(((a.R + rpb - 1) / rpb) * a.strips), (unsigned)((a.cout + 3) / 4), (unsigned)((cin + 3) / 4));
   conv_bwd_weight_kernel<K, STRIDE, UP><<<grid, 128, 0, st>>>(a);
   DQ_LAUNCH_CHECK();
   return 0;
@@ -475,7 +479,7 @@ DQ_API int dq_conv1d_bwd_weight(const float* du, const float* x1, int c1, const 
                                 const float* in_ss, int in_ss_stride, float* dw, float* db, int cout, int K,
                                 int stride, int pad, int up, int R, int Lin, int Lout, int rows_per_sample,
                                 void* stream) {
-  ConvBwdWeightArgs a{du, x1, x2, in_ss, dw, db, c1, c2, cout, R, Lin, Lout, pad, 1, rows_per_sample, in_ss_stride};
+  ConvBwdWeightArgs a{du, x1, x2, in_ss, dw, db, c1, c2, cout, R, Lin, Lout, pad, 1, rows_per_sample, in_ss_stride, Lout, 1};
   cudaStream_t st = (cudaStream_t)stream;
   if (R <= 0 || Lout <= 0) return 0;
   if (K == 3 && stride == 1 && up == 1) return launch_bwd_weight<3, 1, 1>(a, st);

@@ -10,39 +10,10 @@
 // 32 positions is staged in shared memory as [n][132] rows so that (a) a thread writes its own column without
 // conflicts, (b) the 32x32 per-head contractions read float4 broadcasts, (c) the "(n, head)" transposed phases
 // (softmax over d, projections back to C channels) read float4 rows conflict-free.
-#include "common.cuh"
+#include <stdlib.h>
+#include "linattn.cuh"
 
 namespace dq {
-
-constexpr int TP = 32;     // positions per tile
-constexpr int LDS_ = 132;  // padded row stride of the [n][128] staging tiles (floats)
-
-struct LAArgs {
-  const float* x;      // (R, C, L) block input
-  const float* g_pre;  // (C) PreNorm gain
-  const float* wqkv;   // (384, C)
-  const float* wout;   // (C, 128)
-  const float* bout;   // (C)
-  const float* g_out;  // (C)
-  float* part;         // (R, nchunk, 128, 34) forward partials [m, s, ctx[32]]
-  float* ctx;          // (R, 128, 32)  ctx[h*32+d][e]
-  float* ms;           // (R, 128, 2)   max and sum of exp of k over L
-  float* ypre;         // (R, C, L) to_out output before RMSNorm (saved for backward; may be null)
-  float* out;          // (R, C, L)
-  // backward
-  const float* dres;   // (R, C, L) gradient of the block output
-  float* dxnq;         // (R, C, L) scratch: q-path gradient w.r.t. the pre-normed input
-  float* dpart;        // (R, nchunk, 128, 32) partial d ctx
-  float* dctx;         // (R, 128, 32)
-  float* sd;           // (R, 128)   sum_e dctx*ctx
-  float* dx;           // (R, C, L)
-  float* dwqkv;        // (384, C) accumulated
-  float* dwout;        // (C, 128) accumulated
-  float* dbout;        // (C) accumulated
-  float* dg_out;       // (C) accumulated
-  float* dg_pre;       // (C) accumulated
-  int R, L, chunk, nchunk;
-};
 
 // normalise TP positions of row r starting at n0 into xn_s[n][c]; invalid positions give zeros.
 template <int C>
@@ -609,6 +580,9 @@ __global__ void __launch_bounds__(128) la_bwd_kv_kernel(LAArgs a) {
   }
 }
 
+void la_combine_launch(const LAArgs& a, cudaStream_t st) { la_combine_kernel<<<(unsigned)a.R, 128, 0, st>>>(a); }
+void la_bwd_combine_launch(const LAArgs& a, cudaStream_t st) { la_bwd_combine_kernel<<<(unsigned)a.R, 128, 0, st>>>(a); }
+
 template <int C>
 static int la_fwd_launch(const LAArgs& a, cudaStream_t st) {
   dim3 grid((unsigned)a.nchunk, (unsigned)a.R);
@@ -648,6 +622,13 @@ static int la_bwd_launch(const LAArgs& a, cudaStream_t st) {
 
 using namespace dq;
 
+// DQ_LA_FP32=1 selects the fp32 CUDA-core kernels (kept as an on-device cross-check of the tensor-core kernels)
+static bool la_use_fp32() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DQ_LA_FP32"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 // chunking policy shared by forward and backward (the Python side sizes `part`/`dpart` from dq_la_nchunk)
 static int la_chunk(int L) {
   int chunk = 2048;
@@ -665,6 +646,7 @@ DQ_API int dq_linattn_fwd(const float* x, const float* g_pre, const float* wqkv,
   a.R = R; a.L = L; a.chunk = la_chunk(L); a.nchunk = (L + a.chunk - 1) / a.chunk;
   cudaStream_t st = (cudaStream_t)stream;
   if (R <= 0 || L <= 0) return 0;
+  if (!la_use_fp32()) return la_fwd_tc_dispatch(a, C, st);
   switch (C) {
     case 4: return la_fwd_launch<4>(a, st);
     case 8: return la_fwd_launch<8>(a, st);
@@ -688,6 +670,7 @@ DQ_API int dq_linattn_bwd(const float* x, const float* dres, const float* ypre, 
   a.R = R; a.L = L; a.chunk = la_chunk(L); a.nchunk = (L + a.chunk - 1) / a.chunk;
   cudaStream_t st = (cudaStream_t)stream;
   if (R <= 0 || L <= 0) return 0;
+  if (!la_use_fp32()) return la_bwd_tc_dispatch(a, C, st);
   switch (C) {
     case 4: return la_bwd_launch<4>(a, st);
     case 8: return la_bwd_launch<8>(a, st);
