@@ -1,253 +1,485 @@
 // Fused LinearAttention (reference /root/reference/dquartic/model/unet1d.py:473-496, wrapped as
 // Residual(PreNorm(.)) at 1017/1068): out = x + RMSNorm_out(W_out . attn(RMSNorm_pre(x)) + b_out).
 //
-// Nothing of size 384 x L is ever materialised: q/k/v are recomputed from the C-channel input tile by tile.
-//   forward : la_stats (per-chunk online-softmax partials of k and of ctx = softmax_L(k) v^T)
-//             -> la_combine (per row: max, sum, ctx[4][32][32]) -> la_out (q softmax, ctx^T q, to_out, norm, +x)
-//   backward: la_bwd_q (d to_out, d ctx partials, d q-path -> d xn_q) -> la_bwd_combine
-//             -> la_bwd_kv (d k-softmax, d v, d xn, RMSNorm_pre backward, + residual gradient)
-// Mapping: 128 threads per CTA, thread j owns q/k/v channel j = (head h = j/32 = its warp, d = j%32); a tile of
-// 32 positions is staged in shared memory as [n][132] rows so that (a) a thread writes its own column without
-// conflicts, (b) the 32x32 per-head contractions read float4 broadcasts, (c) the "(n, head)" transposed phases
-// (softmax over d, projections back to C channels) read float4 rows conflict-free.
-#include <stdlib.h>
-#include "linattn.cuh"
+// Rank-C restructuring.  q, k, v are 1x1 projections of the C-channel (C <= 32) normalised input xn, so every
+// per-head 32 x 32 contraction of the reference factors through C:
+//     ctx[d][e]  = sum_n ks[d][n] v[e][n]           = sum_c Ms[d][c] Wv[e][c],     Ms[d][c] = sum_n ks[d][n] xn[c][n]
+//     y[c'][n]   = sum_e Wout[c'][e] sum_d ctx[d][e] q[d][n] = sum_d G[c'][d] q[d][n],  G = Wout_h ctx_h^T   (C x 32)
+// and likewise in the backward pass (Gq[d][c'] = sum_n q[d][n] dy[c'][n], H[d][c] = sum_e dctx[d][e] Wv[e][c]).
+// Per position and head the work is a handful of 32 x C products instead of 32 x 32 ones, nothing of size
+// 128 x L (let alone 384 x L) is ever materialised, and the v projection disappears from the per-position loops.
+//
+//   forward : la_stats  (per chunk: online softmax_L(k) partials  m, s, M[d][c] = sum_n exp(k-m) xn)
+//             la_combine (per row: m, s, Ms = M/s, G)
+//             la_out    (q = softmax_d(Wq xn) * scale, y = sum_h G_h q_h + b, RMSNorm_out, + x)
+//   backward: la_bwd_q  (dy = RMSNorm_out backward; dq = G^T dy; softmax backward; d xn_q; partial Gq, dWq)
+//             la_bwd_combine (per row: ctx, dctx, sd, H; dWout, dWv)
+//             la_bwd_kv (ks, dks = H xn, d k_raw, d xn = Wk^T dk + H^T ks + d xn_q, RMSNorm_pre backward, + dres; dWk)
+//
+// Tensor cores: mma.sync m16n8k8 TF32 (fp32 accumulate), one warp = one head, all per-position intermediates in
+// MMA register fragments; the accumulator fragment of one MMA is re-used directly as the A operand of the next.
+// (tcgen05 does not fit: the contraction dims are C = 4..16 and the products are block-diagonal per (row, head) —
+// a 128 x N x 16 tcgen05 tile would be >= 75 % padding and its TMEM round trip costs more than the math.)
+//
+// Fragment conventions (PTX m16n8k8 .tf32, g = lane/4, t = lane%4):
+//   C/D: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+//   A  : a0 (g, k=t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4)        B: b0 (k=t, n=g) b1 (k=t+4, n=g)
+// We use a fixed permutation of the k index inside every k8 block: slot t <-> actual k = 2t, slot t+4 <-> 2t+1.
+// Then (c0, c2, c1, c3) of an accumulator tile IS an A fragment and operands that come from memory are loaded
+// with the same permutation (one 64-bit load).
+#include "common.cuh"
 
 namespace dq {
 
-// normalise TP positions of row r starting at n0 into xn_s[n][c]; invalid positions give zeros.
-template <int C>
-__device__ __forceinline__ void load_xn_tile(const float* __restrict__ x, const float* __restrict__ g, int r, int L,
-                                             int n0, int nend, float* xn_s, float* inv_s) {
-  if (threadIdx.x < TP) {
-    int n = n0 + threadIdx.x;
-    float v[C];
-    float s2 = 0.f;
-    bool ok = n < nend;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      v[c] = ok ? __ldg(x + ((size_t)r * C + c) * L + n) : 0.f;
-      s2 = fmaf(v[c], v[c], s2);
-    }
-    float inv = 1.f / fmaxf(sqrtf(s2), 1e-12f);
-    float sc = inv * sqrtf((float)C);
-#pragma unroll
-    for (int c = 0; c < C; ++c) xn_s[threadIdx.x * C + c] = v[c] * sc * g[c];
-    if (inv_s) inv_s[threadIdx.x] = inv;
-  }
-}
+struct LAArgs {
+  const float* x;      // (R, C, L) block input
+  const float* g_pre;  // (C) PreNorm gain
+  const float* wqkv;   // (384, C)
+  const float* wout;   // (C, 128)
+  const float* bout;   // (C)
+  const float* g_out;  // (C)
+  float* part;         // (R, nchunk, 128, 2+CP) forward partials [m, s, M[CP]]
+  float* msm;          // (R, 128, 2+CP)  [m, s, Ms[CP]]  saved for backward
+  float* gmat;         // (R, C, 128)     G[c'][h*32+d]    saved for backward
+  float* ypre;         // (R, C, L) to_out output before RMSNorm (saved for backward; may be null)
+  float* out;          // (R, C, L)
+  // backward
+  const float* dres;   // (R, C, L) gradient of the block output
+  float* dxnq;         // (R, C, L) scratch: q-path gradient w.r.t. the pre-normed input
+  float* dpart;        // (R, nchunk, 128, CP) partial Gq
+  float* hmat;         // (R, 128, CP)  H[h*32+d][c]
+  float* sd;           // (R, 128)      sum_e dctx*ctx
+  float* dx;           // (R, C, L)
+  float* dwqkv;        // (384, C) accumulated
+  float* dwout;        // (C, 128) accumulated
+  float* dbout;        // (C) accumulated
+  float* dg_out;       // (C) accumulated
+  float* dg_pre;       // (C) accumulated
+  int R, L, chunk, nchunk;
+};
 
 template <int C>
-__device__ __forceinline__ float dotC(const float (&w)[C], const float* __restrict__ xs) {
-  float a = 0.f;
-  if constexpr (C % 4 == 0) {
+struct TC {
+  static constexpr int KC = (C + 7) / 8;                              // k8 steps over the C input channels
+  static constexpr int CP = KC * 8;                                   // padded channel count
+  static constexpr int XS = (CP == 8) ? 8 : (CP <= 24 ? 24 : 40);     // [pos][c] row stride: = 8 or 24 (mod 32)
+  static constexpr int CT = KC;                                       // n8 tiles over C output channels
+  static constexpr int PS = 2 + CP;                                   // partial record: m, s, M[CP]
+  static constexpr int YS = C;                                        // row stride of per-head [pos][c] partial tiles (only c < C stored)
+};
+constexpr int SP = 128;  // positions per staged sub-tile (= threads per CTA)
+constexpr int XT = 136;  // row stride of the transposed [c][pos] tiles (= 8 mod 32: 64-bit fragment loads conflict-free)
+constexpr int RS = 36;   // row stride of the warp-private 16 x 32 transpose tiles
+constexpr float kLazy = 8.f;  // online-softmax rescale threshold (numerators stay <= e^8)
+
+__device__ __forceinline__ uint32_t f2tf(float x) {  // exact round-to-nearest TF32 (used outside the hot loops)
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+// The TF32 MMA ignores the low 13 mantissa bits of its operands (truncation).  Adding half an ulp first makes that
+// truncation a round-to-nearest (ties away) in ONE integer instruction; cvt.rna.tf32 compiles to two plus a NaN test.
+__device__ __forceinline__ uint32_t rtf(float x) { return __float_as_uint(x) + 0x1000u; }
+__device__ __forceinline__ float fexp2(float x) {  // single MUFU.EX2 (no denormal fix-up code)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kTfBias = 7.0444e-4f;           // log2(1 + 2^-11): pre-scaling a value by (1 + 2^-11) un-biases the
+constexpr float kTfBiasMul = 1.00048828125f;    // MMA's operand truncation when it can be folded into an existing op
+__device__ __forceinline__ void mma8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                     uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// d = a b (zero accumulator input: no register zeroing)
+__device__ __forceinline__ void mma8_z(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                       uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
+// A operand of the next MMA from an accumulator tile whose elements already carry TF32-ready bit patterns
+// (rows g / g+8, cols 2t / 2t+1; k = its columns)
+__device__ __forceinline__ void mma8_acc(float (&d)[4], const uint32_t (&v)[4], uint32_t b0, uint32_t b1) {
+  mma8(d, v[0], v[2], v[1], v[3], b0, b1);
+}
+__device__ __forceinline__ void mma8_acc_z(float (&d)[4], const uint32_t (&v)[4], uint32_t b0, uint32_t b1) {
+  mma8_z(d, v[0], v[2], v[1], v[3], b0, b1);
+}
+// d (+)= A[ks] B[ks] over the KC k8 steps of the C input channels, starting from zero
+template <int KC>
+__device__ __forceinline__ void mma_kc(float (&d)[4], const uint32_t (&a)[KC][4], const uint32_t (&b)[KC][2]) {
+  mma8_z(d, a[0][0], a[0][1], a[0][2], a[0][3], b[0][0], b[0][1]);
 #pragma unroll
-    for (int c4 = 0; c4 < C / 4; ++c4) {
-      float4 t = *reinterpret_cast<const float4*>(xs + c4 * 4);
-      a = fmaf(w[c4 * 4 + 0], t.x, a);
-      a = fmaf(w[c4 * 4 + 1], t.y, a);
-      a = fmaf(w[c4 * 4 + 2], t.z, a);
-      a = fmaf(w[c4 * 4 + 3], t.w, a);
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < C; ++c) a = fmaf(w[c], xs[c], a);
-  }
-  return a;
+  for (int ks = 1; ks < KC; ++ks) mma8(d, a[ks][0], a[ks][1], a[ks][2], a[ks][3], b[ks][0], b[ks][1]);
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
-// acc[e] += a * row[e], e in [0,32), row 16-byte aligned in shared memory (broadcast reads)
-__device__ __forceinline__ void axpy32(float (&acc)[32], float a, const float* __restrict__ row) {
+// Thread j normalises position n0 + j (RMSNorm over C with gain g) and writes the TF32-rounded row xn_s[j][0..CP)
+// and column xnT_s[0..CP)[j]; invalid positions give zeros.
+template <int C>
+__device__ __forceinline__ void stage_xn(const float* __restrict__ x, const float* __restrict__ g, int r, int L, int n0,
+                                         int n_end, float* xn_s, float* xnT_s, float* inv_s) {
+  using T = TC<C>;
+  const int j = threadIdx.x, n = n0 + j;
+  const bool ok = n < n_end;
+  float v[T::CP];
+  float s2 = 0.f;
 #pragma unroll
-  for (int e4 = 0; e4 < 8; ++e4) {
-    float4 t = *reinterpret_cast<const float4*>(row + e4 * 4);
-    acc[e4 * 4 + 0] = fmaf(a, t.x, acc[e4 * 4 + 0]);
-    acc[e4 * 4 + 1] = fmaf(a, t.y, acc[e4 * 4 + 1]);
-    acc[e4 * 4 + 2] = fmaf(a, t.z, acc[e4 * 4 + 2]);
-    acc[e4 * 4 + 3] = fmaf(a, t.w, acc[e4 * 4 + 3]);
+  for (int c = 0; c < T::CP; ++c) {
+    v[c] = (c < C && ok) ? __ldg(x + ((size_t)r * C + (c < C ? c : 0)) * L + n) : 0.f;
+    s2 = fmaf(v[c], v[c], s2);
+  }
+  const float inv = 1.f / fmaxf(sqrtf(s2), 1e-12f);
+  const float sc = inv * sqrtf((float)C);
+#pragma unroll
+  for (int c = 0; c < T::CP; ++c) v[c] = (c < C) ? __uint_as_float(rtf(v[c] * sc * __ldg(g + (c < C ? c : 0)))) : 0.f;
+  float4* row = reinterpret_cast<float4*>(xn_s + j * T::XS);
+#pragma unroll
+  for (int c4 = 0; c4 < T::CP / 4; ++c4) row[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+  if (xnT_s) {
+#pragma unroll
+    for (int c = 0; c < T::CP; ++c) xnT_s[c * XT + j] = v[c];
+  }
+  if (inv_s) inv_s[j] = inv;
+}
+
+// B fragments of X^T (k = channel, n = position) for the two n8 tiles of slab s:  bx[j][ks] = {xn[pos][8ks+2t], [..+1]}
+template <int C>
+__device__ __forceinline__ void load_bx(const float* xn_s, int s, int g, int t, uint32_t (&bx)[2][TC<C>::KC][2]) {
+  using T = TC<C>;
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int ks = 0; ks < T::KC; ++ks) {
+      float2 v = *reinterpret_cast<const float2*>(xn_s + (16 * s + 8 * j + g) * T::XS + 8 * ks + 2 * t);
+      bx[j][ks][0] = __float_as_uint(v.x);
+      bx[j][ks][1] = __float_as_uint(v.y);
+    }
+}
+// A fragments of X (rows = positions g, g+8 of slab s; k = channel)
+template <int C>
+__device__ __forceinline__ void load_ax(const float* xn_s, int s, int g, int t, uint32_t (&ax)[TC<C>::KC][4]) {
+  using T = TC<C>;
+#pragma unroll
+  for (int ks = 0; ks < T::KC; ++ks) {
+    float2 lo = *reinterpret_cast<const float2*>(xn_s + (16 * s + g) * T::XS + 8 * ks + 2 * t);
+    float2 hi = *reinterpret_cast<const float2*>(xn_s + (16 * s + 8 + g) * T::XS + 8 * ks + 2 * t);
+    ax[ks][0] = __float_as_uint(lo.x); ax[ks][2] = __float_as_uint(lo.y);
+    ax[ks][1] = __float_as_uint(hi.x); ax[ks][3] = __float_as_uint(hi.y);
   }
 }
-__device__ __forceinline__ float dot32(const float (&w)[32], const float* __restrict__ row) {
-  float a0 = 0.f, a1 = 0.f;
+// B fragments of X (k = position inside k8 block j of slab s, n = channel) from the transposed tile
+template <int C>
+__device__ __forceinline__ void load_bT(const float* xT_s, int s, int j, int g, int t, uint32_t (&b)[TC<C>::CT][2]) {
+  using T = TC<C>;
 #pragma unroll
-  for (int e4 = 0; e4 < 8; ++e4) {
-    float4 t = *reinterpret_cast<const float4*>(row + e4 * 4);
-    a0 = fmaf(w[e4 * 4 + 0], t.x, a0);
-    a1 = fmaf(w[e4 * 4 + 1], t.y, a1);
-    a0 = fmaf(w[e4 * 4 + 2], t.z, a0);
-    a1 = fmaf(w[e4 * 4 + 3], t.w, a1);
+  for (int ct = 0; ct < T::CT; ++ct) {
+    float2 v = *reinterpret_cast<const float2*>(xT_s + (8 * ct + g) * XT + 16 * s + 8 * j + 2 * t);
+    b[ct][0] = __float_as_uint(v.x);
+    b[ct][1] = __float_as_uint(v.y);
   }
-  return a0 + a1;
+}
+// store a tile set v[4][4] (rows = positions g / g+8 of the slab, cols = channel 8*tile + 2t, +1)
+__device__ __forceinline__ void store_tile16x32(float* scr, const uint32_t (&v)[4][4], int g, int t) {
+#pragma unroll
+  for (int dt = 0; dt < 4; ++dt) {
+    *reinterpret_cast<uint2*>(scr + g * RS + 8 * dt + 2 * t) = make_uint2(v[dt][0], v[dt][1]);
+    *reinterpret_cast<uint2*>(scr + (g + 8) * RS + 8 * dt + 2 * t) = make_uint2(v[dt][2], v[dt][3]);
+  }
+}
+// A fragment of the TRANSPOSED tile: rows = channels 16*mt + g (+8), k = positions 8*j + 2t (+1)
+__device__ __forceinline__ void load_At(const float* scr, int mt, int j, int g, int t, uint32_t (&A)[4]) {
+  const uint32_t* p0 = reinterpret_cast<const uint32_t*>(scr) + (8 * j + 2 * t) * RS + 16 * mt + g;
+  A[0] = p0[0]; A[1] = p0[8]; A[2] = p0[RS]; A[3] = p0[RS + 8];
+}
+// softmax over the 32 columns (4 n8 tiles) of rows g and g+8, times `scale`, in place
+__device__ __forceinline__ void softmax_rows(float (&q)[4][4], float scale) {
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int dt = 0; dt < 4; ++dt) mx = fmaxf(mx, fmaxf(q[dt][2 * hf], q[dt][2 * hf + 1]));
+    const float nm = -quad_max(mx) * kLog2e;
+    float sm = 0.f;
+#pragma unroll
+    for (int dt = 0; dt < 4; ++dt) {
+      q[dt][2 * hf] = fexp2(fmaf(q[dt][2 * hf], kLog2e, nm));
+      q[dt][2 * hf + 1] = fexp2(fmaf(q[dt][2 * hf + 1], kLog2e, nm));
+      sm += q[dt][2 * hf] + q[dt][2 * hf + 1];
+    }
+    const float f = __fdividef(scale, quad_sum(sm));
+#pragma unroll
+    for (int dt = 0; dt < 4; ++dt) { q[dt][2 * hf] *= f; q[dt][2 * hf + 1] *= f; }
+  }
+}
+__device__ __forceinline__ void round_tile(const float (&v)[4][4], uint32_t (&o)[4][4]) {
+#pragma unroll
+  for (int dt = 0; dt < 4; ++dt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[dt][i] = rtf(v[dt][i]);
 }
 
 // ------------------------------------------------------------------------------------------- forward: stats
+// K^T = Wk_h X^T as (32 channels x 16 positions) accumulator tiles; softmax over positions is a row-wise online
+// softmax with a lazy rescale; M[d][c] += P[d][n] Xn[n][c] re-uses the K^T accumulators as the A operand.
+// The numerators carry a (1 + 2^-11) factor (folded into the exponent) so that the MMA's operand truncation is
+// unbiased; the same factor is in s, so it cancels in Ms = M / s up to the rounding of the individual terms.
+template <int C, bool FULL>
+__device__ __forceinline__ void stats_slab(const float* xn_s, const float* xnT_s, int s, int g, int t, int n_left,
+                                           const uint32_t (&wk)[2][TC<C>::KC][4], float (&m_run)[2][2],
+                                           float (&nm2)[2][2], float (&s_run)[2][2], float (&Macc)[2][TC<C>::CT][4]) {
+  using T = TC<C>;
+  uint32_t bx[2][T::KC][2];
+  load_bx<C>(xn_s, s, g, t, bx);
+  float kacc[2][2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) mma_kc<T::KC>(kacc[mt][j], wk[mt], bx[j]);
+  if (!FULL) {  // positions >= n_left (relative to the slab) do not exist: push them to -inf (exp -> 0)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        if (8 * j + 2 * t + i >= n_left) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) { kacc[mt][j][i] = -INFINITY; kacc[mt][j][2 + i] = -INFINITY; }
+        }
+  }
+  // lazy online softmax: rescale only when some row's slab maximum exceeds the running reference by > kLazy
+  float lm[2][2];
+  bool need = false;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      lm[mt][hf] = fmaxf(fmaxf(kacc[mt][0][2 * hf], kacc[mt][0][2 * hf + 1]), fmaxf(kacc[mt][1][2 * hf], kacc[mt][1][2 * hf + 1]));
+      need |= lm[mt][hf] > m_run[mt][hf] + kLazy;
+    }
+  if (__any_sync(0xffffffffu, need)) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const float m_new = fmaxf(m_run[mt][hf], quad_max(lm[mt][hf]));
+        const float f = fexp2((m_run[mt][hf] - m_new) * kLog2e);  // exp(-inf) = 0 on the first slab
+        s_run[mt][hf] *= f;
+#pragma unroll
+        for (int ct = 0; ct < T::CT; ++ct) { Macc[mt][ct][2 * hf] *= f; Macc[mt][ct][2 * hf + 1] *= f; }
+        m_run[mt][hf] = m_new;
+        nm2[mt][hf] = fmaf(-m_new, kLog2e, kTfBias);
+      }
+  }
+  uint32_t pk[2][2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float p = fexp2(fmaf(kacc[mt][j][i], kLog2e, nm2[mt][i >> 1]));
+        s_run[mt][i >> 1] += p;
+        pk[mt][j][i] = __float_as_uint(p);
+      }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    uint32_t bt[T::CT][2];
+    load_bT<C>(xnT_s, s, j, g, t, bt);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int ct = 0; ct < T::CT; ++ct) mma8_acc(Macc[mt][ct], pk[mt][j], bt[ct][0], bt[ct][1]);
+  }
+}
+
 template <int C>
 __global__ void __launch_bounds__(128) la_stats_kernel(LAArgs a) {
-  __shared__ __align__(16) float xn_s[TP * C];
-  __shared__ __align__(16) float v_s[TP * LDS_];
-  const int j = threadIdx.x, h = j >> 5;
+  using T = TC<C>;
+  __shared__ __align__(16) float xn_s[SP * T::XS];
+  __shared__ __align__(16) float xnT_s[T::CP * XT];
+  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int r = blockIdx.y, ch = blockIdx.x;
   const int n_begin = ch * a.chunk, n_end = min(a.L, n_begin + a.chunk);
-  float wk[C], wv[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    wk[c] = a.wqkv[(size_t)(kHD + j) * C + c];
-    wv[c] = a.wqkv[(size_t)(2 * kHD + j) * C + c];
-  }
-  float m = -INFINITY, s = 0.f;
-  float ctx[32];
-#pragma unroll
-  for (int e = 0; e < 32; ++e) ctx[e] = 0.f;
 
-  for (int n0 = n_begin; n0 < n_end; n0 += TP) {
-    load_xn_tile<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, nullptr);
+  uint32_t wk[2][T::KC][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < T::KC; ++ks)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = h * 32 + 16 * mt + g + 8 * (i & 1), c = 8 * ks + 2 * t + (i >> 1);
+        wk[mt][ks][i] = f2tf(c < C ? a.wqkv[(size_t)(kHD + d) * C + c] : 0.f);
+      }
+  float m_run[2][2], nm2[2][2], s_run[2][2], Macc[2][T::CT][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    m_run[mt][0] = m_run[mt][1] = -INFINITY;
+    nm2[mt][0] = nm2[mt][1] = 0.f;
+    s_run[mt][0] = s_run[mt][1] = 0.f;
+#pragma unroll
+    for (int ct = 0; ct < T::CT; ++ct)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Macc[mt][ct][i] = 0.f;
+  }
+
+  for (int n0 = n_begin; n0 < n_end; n0 += SP) {
+    stage_xn<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, xnT_s, nullptr);
     __syncthreads();
-    float kreg[TP];
-    float tmax = -INFINITY;
-    const int nv = min(TP, n_end - n0);
-#pragma unroll
-    for (int n = 0; n < TP; ++n) {
-      float kv = dotC<C>(wk, xn_s + n * C);
-      float vv = dotC<C>(wv, xn_s + n * C);
-      kv = (n < nv) ? kv : -INFINITY;
-      kreg[n] = kv;
-      tmax = fmaxf(tmax, kv);
-      v_s[n * LDS_ + j] = vv;
-    }
-    float m_new = fmaxf(m, tmax);
-    float f = __expf(m - m_new);  // exp(-inf) = 0 on the first tile
-    s *= f;
-#pragma unroll
-    for (int e = 0; e < 32; ++e) ctx[e] *= f;
-    m = m_new;
-    __syncthreads();
-#pragma unroll
-    for (int n = 0; n < TP; ++n) {
-      float p = __expf(kreg[n] - m);
-      s += p;
-      axpy32(ctx, p, v_s + n * LDS_ + h * 32);
-    }
+    const int nfull = min(SP, n_end - n0) / 16, nslab = min(SP / 16, (n_end - n0 + 15) / 16);
+    for (int s = 0; s < nfull; ++s) stats_slab<C, true>(xn_s, xnT_s, s, g, t, 16, wk, m_run, nm2, s_run, Macc);
+    if (nslab > nfull) stats_slab<C, false>(xn_s, xnT_s, nfull, g, t, n_end - n0 - 16 * nfull, wk, m_run, nm2, s_run, Macc);
     __syncthreads();
   }
-  float* po = a.part + (((size_t)r * a.nchunk + ch) * kHD + j) * 34;
-  po[0] = m;
-  po[1] = s;
 #pragma unroll
-  for (int e = 0; e < 32; ++e) po[2 + e] = ctx[e];
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const float s = quad_sum(s_run[mt][hf]);
+      const int d = h * 32 + 16 * mt + 8 * hf + g;
+      float* po = a.part + (((size_t)r * a.nchunk + ch) * kHD + d) * T::PS;
+      if (t == 0) { po[0] = m_run[mt][hf]; po[1] = s; }
+#pragma unroll
+      for (int ct = 0; ct < T::CT; ++ct)
+        *reinterpret_cast<float2*>(po + 2 + 8 * ct + 2 * t) = make_float2(Macc[mt][ct][2 * hf], Macc[mt][ct][2 * hf + 1]);
+    }
 }
 
+// per row: m, s, Ms = M / s, ctx (registers only), G[c'][h*32+d] = sum_e Wout[c'][h*32+e] ctx[d][e]
+template <int C>
 __global__ void __launch_bounds__(128) la_combine_kernel(LAArgs a) {
-  const int j = threadIdx.x, r = blockIdx.x;
-  const float* p = a.part + ((size_t)r * a.nchunk * kHD + j) * 34;
+  using T = TC<C>;
+  const int j = threadIdx.x, h = j >> 5, r = blockIdx.x;
+  const float* p = a.part + ((size_t)r * a.nchunk * kHD + j) * T::PS;
   float M = -INFINITY;
-  for (int ch = 0; ch < a.nchunk; ++ch) M = fmaxf(M, p[(size_t)ch * kHD * 34]);
-  float S = 0.f, ctx[32];
+  for (int ch = 0; ch < a.nchunk; ++ch) M = fmaxf(M, p[(size_t)ch * kHD * T::PS]);
+  float S = 0.f, ms[C];
 #pragma unroll
-  for (int e = 0; e < 32; ++e) ctx[e] = 0.f;
+  for (int c = 0; c < C; ++c) ms[c] = 0.f;
   for (int ch = 0; ch < a.nchunk; ++ch) {
-    const float* q = p + (size_t)ch * kHD * 34;
-    float f = __expf(q[0] - M);
+    const float* q = p + (size_t)ch * kHD * T::PS;
+    const float f = fexp2((q[0] - M) * kLog2e);
     S = fmaf(q[1], f, S);
 #pragma unroll
-    for (int e = 0; e < 32; ++e) ctx[e] = fmaf(q[2 + e], f, ctx[e]);
+    for (int c = 0; c < C; ++c) ms[c] = fmaf(q[2 + c], f, ms[c]);
   }
-  float inv = 1.f / S;
-  float* co = a.ctx + ((size_t)r * kHD + j) * 32;
+  const float inv = 1.f / S;
+  float* mo = a.msm + ((size_t)r * kHD + j) * T::PS;
+  mo[0] = M;
+  mo[1] = S;
 #pragma unroll
-  for (int e = 0; e < 32; ++e) co[e] = ctx[e] * inv;
-  a.ms[((size_t)r * kHD + j) * 2 + 0] = M;
-  a.ms[((size_t)r * kHD + j) * 2 + 1] = S;
-}
-
-// softmax over the 32 channels of each (n, head) of a staged [n][132] tile, in place, times `scale`.
-__device__ __forceinline__ void tile_softmax_d(float* q_s, float scale) {
-  const int n = threadIdx.x & 31, h = threadIdx.x >> 5;
-  float* row = q_s + n * LDS_ + h * 32;
-  float v[32];
-#pragma unroll
-  for (int e4 = 0; e4 < 8; ++e4) {
-    float4 t = *reinterpret_cast<const float4*>(row + e4 * 4);
-    v[e4 * 4] = t.x; v[e4 * 4 + 1] = t.y; v[e4 * 4 + 2] = t.z; v[e4 * 4 + 3] = t.w;
+  for (int c = 0; c < T::CP; ++c) {
+    if (c < C) ms[c < C ? c : 0] *= inv;
+    mo[2 + c] = (c < C) ? ms[c < C ? c : 0] : 0.f;
   }
-  float mx = v[0];
+  float gacc[C];
 #pragma unroll
-  for (int e = 1; e < 32; ++e) mx = fmaxf(mx, v[e]);
-  float sm = 0.f;
+  for (int c = 0; c < C; ++c) gacc[c] = 0.f;
+  for (int e = 0; e < 32; ++e) {
+    const float* wv = a.wqkv + (size_t)(2 * kHD + h * 32 + e) * C;
+    float cx = 0.f;
 #pragma unroll
-  for (int e = 0; e < 32; ++e) { v[e] = __expf(v[e] - mx); sm += v[e]; }
-  float f = scale / sm;
+    for (int c = 0; c < C; ++c) cx = fmaf(ms[c], __ldg(wv + c), cx);
 #pragma unroll
-  for (int e4 = 0; e4 < 8; ++e4)
-    *reinterpret_cast<float4*>(row + e4 * 4) = make_float4(v[e4 * 4] * f, v[e4 * 4 + 1] * f, v[e4 * 4 + 2] * f, v[e4 * 4 + 3] * f);
+    for (int c = 0; c < C; ++c) gacc[c] = fmaf(__ldg(a.wout + (size_t)c * kHD + h * 32 + e), cx, gacc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) a.gmat[((size_t)r * C + c) * kHD + j] = gacc[c];
 }
 
 // ------------------------------------------------------------------------------------------- forward: output
+// Per 16-position slab and head: Q = X Wq^T (positions x d) -> softmax over d (quad shuffles) -> Y_h = Qs G_h^T,
+// all in fragments; the four heads' Y_h meet in shared memory for bias + RMSNorm + residual.
 template <int C>
 __global__ void __launch_bounds__(128) la_out_kernel(LAArgs a) {
+  using T = TC<C>;
   extern __shared__ float4 dyn_smem4[];
-  float* sm = reinterpret_cast<float*>(dyn_smem4);
-  float* xn_s = sm;                       // TP*C
-  float* q_s = xn_s + TP * C;             // TP*LDS_
-  float* o_s = q_s + TP * LDS_;           // TP*LDS_
-  float* wout_s = o_s + TP * LDS_;        // C*128
-  float* yp_s = wout_s + C * kHD;         // 4*TP*C
-  const int j = threadIdx.x, h = j >> 5, e = j & 31;
+  float* xn_s = reinterpret_cast<float*>(dyn_smem4);  // SP * XS
+  float* yp_s = xn_s + SP * T::XS;                    // 4 * SP * YS
+  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int r = blockIdx.y;
   const int n_begin = blockIdx.x * a.chunk, n_end = min(a.L, n_begin + a.chunk);
   const float scale = rsqrtf((float)kDimHead);
-  float wq[C], ctxT[32];
-#pragma unroll
-  for (int c = 0; c < C; ++c) wq[c] = a.wqkv[(size_t)j * C + c];
-#pragma unroll
-  for (int d = 0; d < 32; ++d) ctxT[d] = a.ctx[((size_t)r * kHD + h * 32 + d) * 32 + e];
-  for (int i = j; i < C * kHD; i += 128) wout_s[i] = a.wout[i];
 
-  for (int n0 = n_begin; n0 < n_end; n0 += TP) {
-    load_xn_tile<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, nullptr);
-    __syncthreads();
-#pragma unroll 4
-    for (int n = 0; n < TP; ++n) q_s[n * LDS_ + j] = dotC<C>(wq, xn_s + n * C);
-    __syncthreads();
-    tile_softmax_d(q_s, scale);
-    __syncthreads();
-#pragma unroll 4
-    for (int n = 0; n < TP; ++n) o_s[n * LDS_ + j] = dot32(ctxT, q_s + n * LDS_ + h * 32);
-    __syncthreads();
-    {  // y[c][n] partial over the 32 channels of quarter qd
-      const int n = j & 31, qd = j >> 5;
-      float yp[C];
+  uint32_t bq[4][T::KC][2], bg[4][T::CT][2];
 #pragma unroll
-      for (int c = 0; c < C; ++c) yp[c] = 0.f;
-      const float* orow = o_s + n * LDS_ + qd * 32;
+  for (int dt = 0; dt < 4; ++dt)
 #pragma unroll
-      for (int e4 = 0; e4 < 8; ++e4) {
-        float4 t = *reinterpret_cast<const float4*>(orow + e4 * 4);
+    for (int ks = 0; ks < T::KC; ++ks)
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          float4 w = *reinterpret_cast<const float4*>(wout_s + c * kHD + qd * 32 + e4 * 4);
-          yp[c] = fmaf(t.x, w.x, fmaf(t.y, w.y, fmaf(t.z, w.z, fmaf(t.w, w.w, yp[c]))));
-        }
+      for (int i = 0; i < 2; ++i) {
+        const int d = h * 32 + 8 * dt + g, c = 8 * ks + 2 * t + i;
+        bq[dt][ks][i] = f2tf(c < C ? a.wqkv[(size_t)d * C + c] : 0.f);
       }
 #pragma unroll
-      for (int c = 0; c < C; ++c) yp_s[(qd * TP + n) * C + c] = yp[c];
+  for (int kd = 0; kd < 4; ++kd)
+#pragma unroll
+    for (int ct = 0; ct < T::CT; ++ct)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = 8 * ct + g;
+        bg[kd][ct][i] = f2tf(c < C ? a.gmat[((size_t)r * C + c) * kHD + h * 32 + 8 * kd + 2 * t + i] : 0.f);
+      }
+
+  for (int n0 = n_begin; n0 < n_end; n0 += SP) {
+    stage_xn<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, nullptr, nullptr);
+    __syncthreads();
+    const int nslab = min(SP / 16, (n_end - n0 + 15) / 16);
+    for (int s = 0; s < nslab; ++s) {
+      uint32_t ax[T::KC][4];
+      load_ax<C>(xn_s, s, g, t, ax);
+      float q[4][4];
+#pragma unroll
+      for (int dt = 0; dt < 4; ++dt) mma_kc<T::KC>(q[dt], ax, bq[dt]);
+      softmax_rows(q, scale * kTfBiasMul);   // q is only an MMA operand here: pre-bias against the truncation
+      float y[T::CT][4];
+#pragma unroll
+      for (int ct = 0; ct < T::CT; ++ct) {
+        mma8_z(y[ct], __float_as_uint(q[0][0]), __float_as_uint(q[0][2]), __float_as_uint(q[0][1]), __float_as_uint(q[0][3]),
+               bg[0][ct][0], bg[0][ct][1]);
+#pragma unroll
+        for (int kd = 1; kd < 4; ++kd)
+          mma8(y[ct], __float_as_uint(q[kd][0]), __float_as_uint(q[kd][2]), __float_as_uint(q[kd][1]), __float_as_uint(q[kd][3]),
+               bg[kd][ct][0], bg[kd][ct][1]);
+      }
+#pragma unroll
+      for (int ct = 0; ct < T::CT; ++ct)
+        if (8 * ct + 2 * t < C) {
+          float* p0 = yp_s + ((size_t)h * SP + 16 * s + g) * T::YS + 8 * ct + 2 * t;
+          *reinterpret_cast<float2*>(p0) = make_float2(y[ct][0], y[ct][1]);
+          *reinterpret_cast<float2*>(p0 + 8 * T::YS) = make_float2(y[ct][2], y[ct][3]);
+        }
     }
     __syncthreads();
-    if (j < TP && n0 + j < n_end) {
-      const int n = n0 + j;
-      float y[C];
-      float s2 = 0.f;
+    {
+      const int j = threadIdx.x, n = n0 + j;
+      if (n < n_end) {
+        float y[C];
+        float s2 = 0.f;
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        y[c] = a.bout[c] + yp_s[(0 * TP + j) * C + c] + yp_s[(1 * TP + j) * C + c] + yp_s[(2 * TP + j) * C + c] +
-               yp_s[(3 * TP + j) * C + c];
-        s2 = fmaf(y[c], y[c], s2);
-      }
-      float sc = sqrtf((float)C) / fmaxf(sqrtf(s2), 1e-12f);
+        for (int c = 0; c < C; ++c) {
+          y[c] = a.bout[c] + yp_s[(0 * SP + j) * T::YS + c] + yp_s[(1 * SP + j) * T::YS + c] +
+                 yp_s[(2 * SP + j) * T::YS + c] + yp_s[(3 * SP + j) * T::YS + c];
+          s2 = fmaf(y[c], y[c], s2);
+        }
+        const float sc = sqrtf((float)C) / fmaxf(sqrtf(s2), 1e-12f);
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        size_t idx = ((size_t)r * C + c) * a.L + n;
-        if (a.ypre) a.ypre[idx] = y[c];
-        a.out[idx] = fmaf(y[c] * sc, a.g_out[c], __ldg(a.x + idx));
+        for (int c = 0; c < C; ++c) {
+          const size_t idx = ((size_t)r * C + c) * a.L + n;
+          if (a.ypre) a.ypre[idx] = y[c];
+          a.out[idx] = fmaf(y[c] * sc, a.g_out[c], __ldg(a.x + idx));
+        }
       }
     }
     __syncthreads();
@@ -255,366 +487,469 @@ __global__ void __launch_bounds__(128) la_out_kernel(LAArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------- backward: q path
+// Per slab and head (fragments): Q -> Qs, dQs = dY G_h, dQr (softmax backward), dXn_q = dQr Wq_h.
+// Reductions over positions (Gq = Qs^T dY, dWq = dQr^T Xn) read Qs / dQr back from warp-private shared tiles in
+// the transposed role.
 template <int C>
 __global__ void __launch_bounds__(128) la_bwd_q_kernel(LAArgs a) {
+  using T = TC<C>;
   extern __shared__ float4 dyn_smem4[];
-  float* sm = reinterpret_cast<float*>(dyn_smem4);
-  float* xn_s = sm;                        // TP*C
-  float* dy_s = xn_s + TP * C;             // TP*C
-  float* q_s = dy_s + TP * C;              // TP*LDS_   q_raw -> q_soft*scale -> d q_raw
-  float* do_s = q_s + TP * LDS_;           // TP*LDS_   d out (128 per position) -> t = qs * dqs
-  float* wq_s = do_s + TP * LDS_;          // 128*C
-  float* yp_s = wq_s + kHD * C;            // 4*TP*C
-  float* tsum_s = yp_s + 4 * TP * C;       // TP*4
-  float* acc_s = tsum_s + TP * 4;          // TP*2*C  per-position-lane partials of d g_out, d b_out
-  const int j = threadIdx.x, h = j >> 5, e = j & 31;
+  float* xn_s = reinterpret_cast<float*>(dyn_smem4);   // SP * XS
+  float* dy_s = xn_s + SP * T::XS;                     // SP * XS
+  float* xnT_s = dy_s + SP * T::XS;                    // CP * XT
+  float* dyT_s = xnT_s + T::CP * XT;                   // CP * XT
+  float* yp_s = dyT_s + T::CP * XT;                    // 4 * SP * YS   per-head d xn_q
+  float* scr = yp_s + 4 * SP * T::YS;                  // 4 warps * 2 tiles * 16 * RS
+  float* acc_s = scr + 4 * 2 * 16 * RS;                // 2 * C  (d g_out, d b_out)
+  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int r = blockIdx.y, ch = blockIdx.x;
   const int n_begin = ch * a.chunk, n_end = min(a.L, n_begin + a.chunk);
-  const float scale = rsqrtf((float)kDimHead);
+  const float scale = rsqrtf((float)kDimHead), inv_scale = sqrtf((float)kDimHead);
   const float sqrtC = sqrtf((float)C);
-  float wq[C], wo[C], dwq[C], dwo[C];
-  float ctxR[32], ctxT[32], dctx[32];
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    wq[c] = a.wqkv[(size_t)j * C + c];
-    wo[c] = a.wout[(size_t)c * kHD + j];
-    dwq[c] = 0.f; dwo[c] = 0.f;
-  }
-#pragma unroll
-  for (int d = 0; d < 32; ++d) {
-    ctxR[d] = a.ctx[((size_t)r * kHD + j) * 32 + d];                 // ctx[h][d=j%32][e=d']
-    ctxT[d] = a.ctx[((size_t)r * kHD + h * 32 + d) * 32 + e];        // ctx[h][d'][e=j%32]
-    dctx[d] = 0.f;
-  }
-  for (int i = j; i < kHD * C; i += 128) wq_s[i] = a.wqkv[i];
-  if (j < TP) {
-#pragma unroll
-    for (int c = 0; c < 2 * C; ++c) acc_s[j * 2 * C + c] = 0.f;
-  }
+  float* scrQ = scr + (h * 2 + 0) * 16 * RS;
+  float* scrR = scr + (h * 2 + 1) * 16 * RS;
 
-  for (int n0 = n_begin; n0 < n_end; n0 += TP) {
-    load_xn_tile<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, nullptr);
-    if (j < TP) {  // d y = RMSNorm_out backward of d res
-      const int n = n0 + j;
+  uint32_t bq[4][T::KC][2], bgA[4][T::KC][2], bqT[4][T::CT][2];
+#pragma unroll
+  for (int dt = 0; dt < 4; ++dt)
+#pragma unroll
+    for (int ks = 0; ks < T::KC; ++ks)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = 8 * ks + 2 * t + i, d = h * 32 + 8 * dt + g;
+        bq[dt][ks][i] = f2tf(c < C ? a.wqkv[(size_t)d * C + c] : 0.f);
+        bgA[dt][ks][i] = f2tf(c < C ? a.gmat[((size_t)r * C + c) * kHD + d] : 0.f);   // B[k = c'][n = d] = G[c'][d]
+      }
+#pragma unroll
+  for (int kd = 0; kd < 4; ++kd)
+#pragma unroll
+    for (int ct = 0; ct < T::CT; ++ct)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = 8 * ct + g;
+        bqT[kd][ct][i] = f2tf(c < C ? a.wqkv[(size_t)(h * 32 + 8 * kd + 2 * t + i) * C + c] : 0.f);
+      }
+  float gq[2][T::CT][4], dwq[2][T::CT][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ct = 0; ct < T::CT; ++ct)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { gq[mt][ct][i] = 0.f; dwq[mt][ct][i] = 0.f; }
+  if (threadIdx.x < 2 * C) acc_s[threadIdx.x] = 0.f;
+  __syncthreads();
+
+  for (int n0 = n_begin; n0 < n_end; n0 += SP) {
+    stage_xn<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, xnT_s, nullptr);
+    {  // d y = RMSNorm_out backward of d res, thread j = position
+      const int j = threadIdx.x, n = n0 + j;
       const bool ok = n < n_end;
       float y[C], dr[C];
       float s2 = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        size_t idx = ((size_t)r * C + c) * a.L + n;
+        const size_t idx = ((size_t)r * C + c) * a.L + n;
         y[c] = ok ? __ldg(a.ypre + idx) : 0.f;
         dr[c] = ok ? __ldg(a.dres + idx) : 0.f;
         s2 = fmaf(y[c], y[c], s2);
       }
-      float nrm = sqrtf(s2);
-      float inv = 1.f / fmaxf(nrm, 1e-12f);
-      float dot = 0.f;
+      const float nrm = sqrtf(s2), inv = 1.f / fmaxf(nrm, 1e-12f);
+      float dot = 0.f, dgl[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        float uh = y[c] * inv;
-        acc_s[j * 2 * C + c] += dr[c] * uh * sqrtC;
-        float duh = dr[c] * a.g_out[c] * sqrtC;
+        const float uh = y[c] * inv;
+        dgl[c] = dr[c] * uh * sqrtC;
+        const float duh = dr[c] * a.g_out[c] * sqrtC;
         dot = fmaf(duh, uh, dot);
         y[c] = uh; dr[c] = duh;
       }
+      float dv[T::CP];
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        float d = (nrm > 1e-12f) ? (dr[c] - y[c] * dot) * inv : dr[c] * inv;
-        d = ok ? d : 0.f;
-        acc_s[j * 2 * C + C + c] += d;
-        dy_s[j * C + c] = d;
+      for (int c = 0; c < T::CP; ++c) {
+        float d = 0.f;
+        if (c < C) {
+          d = (nrm > 1e-12f) ? (dr[c < C ? c : 0] - y[c < C ? c : 0] * dot) * inv : dr[c < C ? c : 0] * inv;
+          d = ok ? d : 0.f;
+          const float s1 = warp_sum(dgl[c < C ? c : 0]), s2b = warp_sum(d);
+          if (lane == 0) { atomicAdd(acc_s + c, s1); atomicAdd(acc_s + C + c, s2b); }
+        }
+        dv[c] = __uint_as_float(rtf(d));
+        dyT_s[c * XT + j] = dv[c];
       }
+      float4* row = reinterpret_cast<float4*>(dy_s + j * T::XS);
+#pragma unroll
+      for (int c4 = 0; c4 < T::CP / 4; ++c4) row[c4] = make_float4(dv[4 * c4], dv[4 * c4 + 1], dv[4 * c4 + 2], dv[4 * c4 + 3]);
     }
     __syncthreads();
-#pragma unroll 4
-    for (int n = 0; n < TP; ++n) {
-      q_s[n * LDS_ + j] = dotC<C>(wq, xn_s + n * C);
-      do_s[n * LDS_ + j] = dotC<C>(wo, dy_s + n * C);
-    }
-    __syncthreads();
-    tile_softmax_d(q_s, scale);
-    __syncthreads();
-    float dq[TP];
+    const int nslab = min(SP / 16, (n_end - n0 + 15) / 16);
+    for (int s = 0; s < nslab; ++s) {
+      float qs[4][4], dqs[4][4];
+      {
+        uint32_t ax[T::KC][4];
+        load_ax<C>(xn_s, s, g, t, ax);
 #pragma unroll
-    for (int n = 0; n < TP; ++n) {
-      const float qsv = q_s[n * LDS_ + j];
-      const float* drow = do_s + n * LDS_ + h * 32;
-      // dqs = sum_e ctx[j][e] do[e];  dctx[j][e] += qs * do[e]   (same broadcast loads)
-      float dqs0 = 0.f, dqs1 = 0.f;
+        for (int dt = 0; dt < 4; ++dt) mma_kc<T::KC>(qs[dt], ax, bq[dt]);
+        load_ax<C>(dy_s, s, g, t, ax);
 #pragma unroll
-      for (int e4 = 0; e4 < 8; ++e4) {
-        float4 t = *reinterpret_cast<const float4*>(drow + e4 * 4);
-        dqs0 = fmaf(ctxR[e4 * 4 + 0], t.x, dqs0);
-        dqs1 = fmaf(ctxR[e4 * 4 + 1], t.y, dqs1);
-        dqs0 = fmaf(ctxR[e4 * 4 + 2], t.z, dqs0);
-        dqs1 = fmaf(ctxR[e4 * 4 + 3], t.w, dqs1);
-        dctx[e4 * 4 + 0] = fmaf(qsv, t.x, dctx[e4 * 4 + 0]);
-        dctx[e4 * 4 + 1] = fmaf(qsv, t.y, dctx[e4 * 4 + 1]);
-        dctx[e4 * 4 + 2] = fmaf(qsv, t.z, dctx[e4 * 4 + 2]);
-        dctx[e4 * 4 + 3] = fmaf(qsv, t.w, dctx[e4 * 4 + 3]);
+        for (int dt = 0; dt < 4; ++dt) mma_kc<T::KC>(dqs[dt], ax, bgA[dt]);
       }
-      dq[n] = dqs0 + dqs1;
-      // out[j=(h,e)][n] for d W_out
-      float o = dot32(ctxT, q_s + n * LDS_ + h * 32);
-      const float* dyr = dy_s + n * C;
+      softmax_rows(qs, scale);
+      uint32_t rq[4][4];
+      round_tile(qs, rq);
+      store_tile16x32(scrQ, rq, g, t);
+      // softmax backward: dQr = Qs * (dQs - sum_d Qs dQs / scale)
 #pragma unroll
-      for (int c = 0; c < C; ++c) dwo[c] = fmaf(dyr[c], o, dwo[c]);
+      for (int hf = 0; hf < 2; ++hf) {
+        float ts = 0.f;
+#pragma unroll
+        for (int dt = 0; dt < 4; ++dt) ts += qs[dt][2 * hf] * dqs[dt][2 * hf] + qs[dt][2 * hf + 1] * dqs[dt][2 * hf + 1];
+        ts = quad_sum(ts) * inv_scale;
+#pragma unroll
+        for (int dt = 0; dt < 4; ++dt) {
+          dqs[dt][2 * hf] = qs[dt][2 * hf] * (dqs[dt][2 * hf] - ts);
+          dqs[dt][2 * hf + 1] = qs[dt][2 * hf + 1] * (dqs[dt][2 * hf + 1] - ts);
+        }
+      }
+      round_tile(dqs, rq);
+      store_tile16x32(scrR, rq, g, t);
+      {  // d xn_q (this head) = dQr Wq_h
+        float dxn[T::CT][4];
+#pragma unroll
+        for (int ct = 0; ct < T::CT; ++ct) {
+          mma8_acc_z(dxn[ct], rq[0], bqT[0][ct][0], bqT[0][ct][1]);
+#pragma unroll
+          for (int kd = 1; kd < 4; ++kd) mma8_acc(dxn[ct], rq[kd], bqT[kd][ct][0], bqT[kd][ct][1]);
+        }
+#pragma unroll
+        for (int ct = 0; ct < T::CT; ++ct)
+          if (8 * ct + 2 * t < C) {
+            float* p0 = yp_s + ((size_t)h * SP + 16 * s + g) * T::YS + 8 * ct + 2 * t;
+            *reinterpret_cast<float2*>(p0) = make_float2(dxn[ct][0], dxn[ct][1]);
+            *reinterpret_cast<float2*>(p0 + 8 * T::YS) = make_float2(dxn[ct][2], dxn[ct][3]);
+          }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint32_t Bdy[T::CT][2], Bxn[T::CT][2];
+        load_bT<C>(dyT_s, s, j, g, t, Bdy);
+        load_bT<C>(xnT_s, s, j, g, t, Bxn);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          uint32_t Aq[4], Ar[4];
+          load_At(scrQ, mt, j, g, t, Aq);
+          load_At(scrR, mt, j, g, t, Ar);
+#pragma unroll
+          for (int ct = 0; ct < T::CT; ++ct) {
+            mma8(gq[mt][ct], Aq[0], Aq[1], Aq[2], Aq[3], Bdy[ct][0], Bdy[ct][1]);
+            mma8(dwq[mt][ct], Ar[0], Ar[1], Ar[2], Ar[3], Bxn[ct][0], Bxn[ct][1]);
+          }
+        }
+      }
+      __syncwarp();
     }
-    __syncthreads();  // all reads of do_s done
-#pragma unroll
-    for (int n = 0; n < TP; ++n) do_s[n * LDS_ + j] = q_s[n * LDS_ + j] * dq[n];
     __syncthreads();
     {
-      const int n = j & 31, hh = j >> 5;
-      const float* row = do_s + n * LDS_ + hh * 32;
-      float t = 0.f;
-#pragma unroll
-      for (int e4 = 0; e4 < 8; ++e4) {
-        float4 v = *reinterpret_cast<const float4*>(row + e4 * 4);
-        t += (v.x + v.y) + (v.z + v.w);
-      }
-      tsum_s[n * 4 + hh] = t;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int n = 0; n < TP; ++n) {
-      float qsv = q_s[n * LDS_ + j];
-      float dqr = qsv * (dq[n] - tsum_s[n * 4 + h] * (1.f / scale));
-      const float* xr = xn_s + n * C;
-#pragma unroll
-      for (int c = 0; c < C; ++c) dwq[c] = fmaf(dqr, xr[c], dwq[c]);
-      q_s[n * LDS_ + j] = dqr;  // own column only
-    }
-    __syncthreads();
-    {  // d xn_q[c][n] = sum_j wq[j][c] dqr[j][n]
-      const int n = j & 31, qd = j >> 5;
-      float yp[C];
-#pragma unroll
-      for (int c = 0; c < C; ++c) yp[c] = 0.f;
-      const float* qrow = q_s + n * LDS_ + qd * 32;
-#pragma unroll
-      for (int e4 = 0; e4 < 8; ++e4) {
-        float4 t = *reinterpret_cast<const float4*>(qrow + e4 * 4);
-        const float* w0 = wq_s + (qd * 32 + e4 * 4) * C;
+      const int j = threadIdx.x, n = n0 + j;
+      if (n < n_end) {
 #pragma unroll
         for (int c = 0; c < C; ++c)
-          yp[c] = fmaf(t.x, w0[c], fmaf(t.y, w0[C + c], fmaf(t.z, w0[2 * C + c], fmaf(t.w, w0[3 * C + c], yp[c]))));
+          a.dxnq[((size_t)r * C + c) * a.L + n] = yp_s[(0 * SP + j) * T::YS + c] + yp_s[(1 * SP + j) * T::YS + c] +
+                                                  yp_s[(2 * SP + j) * T::YS + c] + yp_s[(3 * SP + j) * T::YS + c];
       }
-#pragma unroll
-      for (int c = 0; c < C; ++c) yp_s[(qd * TP + n) * C + c] = yp[c];
-    }
-    __syncthreads();
-    if (j < TP && n0 + j < n_end) {
-#pragma unroll
-      for (int c = 0; c < C; ++c)
-        a.dxnq[((size_t)r * C + c) * a.L + n0 + j] = yp_s[(0 * TP + j) * C + c] + yp_s[(1 * TP + j) * C + c] +
-                                                     yp_s[(2 * TP + j) * C + c] + yp_s[(3 * TP + j) * C + c];
     }
     __syncthreads();
   }
-  float* dp = a.dpart + (((size_t)r * a.nchunk + ch) * kHD + j) * 32;
+  // Gq partial of this chunk: rows d, cols c'
 #pragma unroll
-  for (int d = 0; d < 32; ++d) dp[d] = dctx[d];
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    atomicAdd(a.dwqkv + (size_t)j * C + c, dwq[c]);
-    atomicAdd(a.dwout + (size_t)c * kHD + j, dwo[c]);
-  }
-  if (j < 32) {
+    for (int hf = 0; hf < 2; ++hf) {
+      float* dp = a.dpart + (((size_t)r * a.nchunk + ch) * kHD + h * 32 + 16 * mt + 8 * hf + g) * T::CP;
+#pragma unroll
+      for (int ct = 0; ct < T::CT; ++ct)
+        *reinterpret_cast<float2*>(dp + 8 * ct + 2 * t) = make_float2(gq[mt][ct][2 * hf], gq[mt][ct][2 * hf + 1]);
+    }
+  // d Wq (rows d, cols c)
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ct = 0; ct < T::CT; ++ct)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = h * 32 + 16 * mt + g + 8 * (i >> 1), c = 8 * ct + 2 * t + (i & 1);
+        if (c < C) atomicAdd(a.dwqkv + (size_t)d * C + c, dwq[mt][ct][i]);
+      }
+  __syncthreads();
+  if (threadIdx.x < C) atomicAdd(a.dg_out + threadIdx.x, acc_s[threadIdx.x]);
+  else if (threadIdx.x < 2 * C) atomicAdd(a.dbout + threadIdx.x - C, acc_s[threadIdx.x]);
+}
+
+// per row: Gq, ctx, dctx, sd, H; dWout and dWv (their reductions over positions collapsed to reductions over d)
+template <int C>
+__global__ void __launch_bounds__(128) la_bwd_combine_kernel(LAArgs a, int rows_per_block) {
+  using T = TC<C>;
+  extern __shared__ float4 dyn_smem4[];
+  float* ctx_s = reinterpret_cast<float*>(dyn_smem4);  // 128 * 33
+  float* dctx_s = ctx_s + kHD * 33;                    // 128 * 33
+  float* gq_s = dctx_s + kHD * 33;                     // 128 * (C + 1)
+  float* ms_s = gq_s + kHD * (C + 1);                  // 128 * (C + 1)
+  const int j = threadIdx.x, h = j >> 5, e = j & 31;
+  float dwo[C], dwv[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) { dwo[c] = 0.f; dwv[c] = 0.f; }
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(a.R, r0 + rows_per_block);
+  for (int r = r0; r < r1; ++r) {
+    float gqv[C], ms[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) gqv[c] = 0.f;
+    for (int ch = 0; ch < a.nchunk; ++ch) {
+      const float* p = a.dpart + (((size_t)r * a.nchunk + ch) * kHD + j) * T::CP;
+#pragma unroll
+      for (int c = 0; c < C; ++c) gqv[c] += p[c];
+    }
+    const float* mp = a.msm + ((size_t)r * kHD + j) * T::PS + 2;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      float s1 = warp_sum(acc_s[j * 2 * C + c]), s2 = warp_sum(acc_s[j * 2 * C + C + c]);
-      if (j == 0) { atomicAdd(a.dg_out + c, s1); atomicAdd(a.dbout + c, s2); }
+      ms[c] = mp[c];
+      gq_s[j * (C + 1) + c] = gqv[c];
+      ms_s[j * (C + 1) + c] = ms[c];
     }
+    float sd = 0.f, hacc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) hacc[c] = 0.f;
+    for (int ee = 0; ee < 32; ++ee) {
+      const float* wv = a.wqkv + (size_t)(2 * kHD + h * 32 + ee) * C;
+      float cx = 0.f, dc = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        cx = fmaf(ms[c], __ldg(wv + c), cx);
+        dc = fmaf(__ldg(a.wout + (size_t)c * kHD + h * 32 + ee), gqv[c], dc);
+      }
+      sd = fmaf(dc, cx, sd);
+#pragma unroll
+      for (int c = 0; c < C; ++c) hacc[c] = fmaf(dc, __ldg(wv + c), hacc[c]);
+      ctx_s[j * 33 + ee] = cx;
+      dctx_s[j * 33 + ee] = dc;
+    }
+    a.sd[(size_t)r * kHD + j] = sd;
+    float* ho = a.hmat + ((size_t)r * kHD + j) * T::CP;
+#pragma unroll
+    for (int c = 0; c < T::CP; ++c) ho[c] = (c < C) ? hacc[c < C ? c : 0] : 0.f;
+    __syncthreads();
+    // thread (h, e): dWout[c'][h*32+e] += sum_d ctx[d][e] Gq[d][c'];  dWv[h*32+e][c] += sum_d dctx[d][e] Ms[d][c]
+    for (int d = 0; d < 32; ++d) {
+      const float cx = ctx_s[(h * 32 + d) * 33 + e], dc = dctx_s[(h * 32 + d) * 33 + e];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        dwo[c] = fmaf(cx, gq_s[(h * 32 + d) * (C + 1) + c], dwo[c]);
+        dwv[c] = fmaf(dc, ms_s[(h * 32 + d) * (C + 1) + c], dwv[c]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    atomicAdd(a.dwout + (size_t)c * kHD + j, dwo[c]);
+    atomicAdd(a.dwqkv + (size_t)(2 * kHD + j) * C + c, dwv[c]);
   }
 }
 
-__global__ void __launch_bounds__(128) la_bwd_combine_kernel(LAArgs a) {
-  const int j = threadIdx.x, r = blockIdx.x;
-  float d[32];
-#pragma unroll
-  for (int e = 0; e < 32; ++e) d[e] = 0.f;
-  for (int ch = 0; ch < a.nchunk; ++ch) {
-    const float* p = a.dpart + (((size_t)r * a.nchunk + ch) * kHD + j) * 32;
-#pragma unroll
-    for (int e = 0; e < 32; ++e) d[e] += p[e];
-  }
-  const float* c = a.ctx + ((size_t)r * kHD + j) * 32;
-  float* o = a.dctx + ((size_t)r * kHD + j) * 32;
-  float sd = 0.f;
-#pragma unroll
-  for (int e = 0; e < 32; ++e) { o[e] = d[e]; sd = fmaf(d[e], c[e], sd); }
-  a.sd[(size_t)r * kHD + j] = sd;
-}
-
-// ------------------------------------------------------------------------------------------- backward: k/v path
+// ------------------------------------------------------------------------------------------- backward: k path
 template <int C>
 __global__ void __launch_bounds__(128) la_bwd_kv_kernel(LAArgs a) {
+  using T = TC<C>;
   extern __shared__ float4 dyn_smem4[];
-  float* sm = reinterpret_cast<float*>(dyn_smem4);
-  float* xn_s = sm;                        // TP*C
-  float* k_s = xn_s + TP * C;              // TP*LDS_
-  float* v_s = k_s + TP * LDS_;            // TP*LDS_
-  float* wk_s = v_s + TP * LDS_;           // 128*C
-  float* wv_s = wk_s + kHD * C;            // 128*C
-  float* yp_s = wv_s + kHD * C;            // 4*TP*C
-  float* inv_s = yp_s + 4 * TP * C;        // TP
-  float* acc_s = inv_s + TP;               // TP*C
-  const int j = threadIdx.x, h = j >> 5, e = j & 31;
+  float* xn_s = reinterpret_cast<float*>(dyn_smem4);   // SP * XS
+  float* xnT_s = xn_s + SP * T::XS;                    // CP * XT
+  float* yp_s = xnT_s + T::CP * XT;                    // 4 * SP * YS
+  float* scr = yp_s + 4 * SP * T::YS;                  // 4 warps * 16 * RS
+  float* inv_s = scr + 4 * 16 * RS;                    // SP
+  float* acc_s = inv_s + SP;                           // C (d g_pre)
+  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int r = blockIdx.y;
   const int n_begin = blockIdx.x * a.chunk, n_end = min(a.L, n_begin + a.chunk);
   const float sqrtC = sqrtf((float)C);
-  float wk[C], wv[C], dwk[C], dwv[C];
-  float dcR[32], dcT[32];
-#pragma unroll
-  for (int c = 0; c < C; ++c) {
-    wk[c] = a.wqkv[(size_t)(kHD + j) * C + c];
-    wv[c] = a.wqkv[(size_t)(2 * kHD + j) * C + c];
-    dwk[c] = 0.f; dwv[c] = 0.f;
-  }
-#pragma unroll
-  for (int d = 0; d < 32; ++d) {
-    dcR[d] = a.dctx[((size_t)r * kHD + j) * 32 + d];           // dctx[h][d=j%32][e']
-    dcT[d] = a.dctx[((size_t)r * kHD + h * 32 + d) * 32 + e];  // dctx[h][d'][e=j%32]
-  }
-  for (int i = j; i < kHD * C; i += 128) {
-    wk_s[i] = a.wqkv[(size_t)kHD * C + i];
-    wv_s[i] = a.wqkv[(size_t)2 * kHD * C + i];
-  }
-  const float M = a.ms[((size_t)r * kHD + j) * 2], Sinv = 1.f / a.ms[((size_t)r * kHD + j) * 2 + 1];
-  const float sdj = a.sd[(size_t)r * kHD + j];
-  if (j < TP) {
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc_s[j * C + c] = 0.f;
-  }
+  float* scrK = scr + h * 16 * RS;
 
-  for (int n0 = n_begin; n0 < n_end; n0 += TP) {
-    load_xn_tile<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, inv_s);
-    __syncthreads();
-    float kown[TP];
+  uint32_t bwk[4][T::KC][2], bh[4][T::KC][2], bkT[4][T::CT][2], bhT[4][T::CT][2];
+  float cn[4][2], cd[4][2];
 #pragma unroll
-    for (int n = 0; n < TP; ++n) {
-      float kr = dotC<C>(wk, xn_s + n * C);
-      float ks = __expf(kr - M) * Sinv;
-      kown[n] = ks;
-      k_s[n * LDS_ + j] = ks;
-      v_s[n * LDS_ + j] = dotC<C>(wv, xn_s + n * C);
-    }
-    __syncthreads();
-    float dkr[TP], dvr[TP];
+  for (int dt = 0; dt < 4; ++dt) {
 #pragma unroll
-    for (int n = 0; n < TP; ++n) {
-      float dks = dot32(dcR, v_s + n * LDS_ + h * 32);
-      float dv = dot32(dcT, k_s + n * LDS_ + h * 32);
-      float dk = kown[n] * (dks - sdj);
-      dkr[n] = dk; dvr[n] = dv;
-      const float* xr = xn_s + n * C;
+    for (int ks = 0; ks < T::KC; ++ks)
 #pragma unroll
-      for (int c = 0; c < C; ++c) { dwk[c] = fmaf(dk, xr[c], dwk[c]); dwv[c] = fmaf(dv, xr[c], dwv[c]); }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int n = 0; n < TP; ++n) { k_s[n * LDS_ + j] = dkr[n]; v_s[n * LDS_ + j] = dvr[n]; }
-    __syncthreads();
-    {
-      const int n = j & 31, qd = j >> 5;
-      float yp[C];
-#pragma unroll
-      for (int c = 0; c < C; ++c) yp[c] = 0.f;
-      const float* krow = k_s + n * LDS_ + qd * 32;
-      const float* vrow = v_s + n * LDS_ + qd * 32;
-#pragma unroll
-      for (int e4 = 0; e4 < 8; ++e4) {
-        float4 tk = *reinterpret_cast<const float4*>(krow + e4 * 4);
-        float4 tv = *reinterpret_cast<const float4*>(vrow + e4 * 4);
-        const float* w0 = wk_s + (qd * 32 + e4 * 4) * C;
-        const float* w1 = wv_s + (qd * 32 + e4 * 4) * C;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          float t = fmaf(tk.x, w0[c], fmaf(tk.y, w0[C + c], fmaf(tk.z, w0[2 * C + c], fmaf(tk.w, w0[3 * C + c], yp[c]))));
-          yp[c] = fmaf(tv.x, w1[c], fmaf(tv.y, w1[C + c], fmaf(tv.z, w1[2 * C + c], fmaf(tv.w, w1[3 * C + c], t))));
-        }
+      for (int i = 0; i < 2; ++i) {
+        const int c = 8 * ks + 2 * t + i, d = h * 32 + 8 * dt + g;
+        bwk[dt][ks][i] = f2tf(c < C ? a.wqkv[(size_t)(kHD + d) * C + c] : 0.f);
+        bh[dt][ks][i] = f2tf(a.hmat[((size_t)r * kHD + d) * T::CP + c]);               // B[k = c][n = d] = H[d][c]
       }
 #pragma unroll
-      for (int c = 0; c < C; ++c) yp_s[(qd * TP + n) * C + c] = yp[c];
+    for (int ct = 0; ct < T::CT; ++ct)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = 8 * ct + g, d = h * 32 + 8 * dt + 2 * t + i;
+        bkT[dt][ct][i] = f2tf(c < C ? a.wqkv[(size_t)(kHD + d) * C + c] : 0.f);        // B[k = d][n = c] = Wk[d][c]
+        bhT[dt][ct][i] = f2tf(a.hmat[((size_t)r * kHD + d) * T::CP + c]);              // B[k = d][n = c] = H[d][c]
+      }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const size_t jd = (size_t)r * kHD + h * 32 + 8 * dt + 2 * t + i;
+      cn[dt][i] = -(a.msm[jd * T::PS] * kLog2e + log2f(a.msm[jd * T::PS + 1]));  // softmax_L(k) = 2^(k log2e + cn)
+      cd[dt][i] = a.sd[jd];
+    }
+  }
+  float dwk[2][T::CT][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ct = 0; ct < T::CT; ++ct)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dwk[mt][ct][i] = 0.f;
+  if (threadIdx.x < C) acc_s[threadIdx.x] = 0.f;
+
+  for (int n0 = n_begin; n0 < n_end; n0 += SP) {
+    stage_xn<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, xnT_s, inv_s);
+    __syncthreads();
+    const int nslab = min(SP / 16, (n_end - n0 + 15) / 16);
+    for (int s = 0; s < nslab; ++s) {
+      float kk[4][4], dks[4][4];
+      {
+        uint32_t ax[T::KC][4];
+        load_ax<C>(xn_s, s, g, t, ax);
+#pragma unroll
+        for (int dt = 0; dt < 4; ++dt) {
+          mma_kc<T::KC>(kk[dt], ax, bwk[dt]);
+          mma_kc<T::KC>(dks[dt], ax, bh[dt]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            kk[dt][i] = fexp2(fmaf(kk[dt][i], kLog2e, cn[dt][i & 1]));   // softmax_L(k)
+            dks[dt][i] = kk[dt][i] * (dks[dt][i] - cd[dt][i & 1]);       // d k_raw
+          }
+        }
+      }
+      uint32_t rk[4][4], rd[4][4];
+      round_tile(kk, rk);
+      round_tile(dks, rd);
+      store_tile16x32(scrK, rd, g, t);
+      {
+        float dxn[T::CT][4];
+#pragma unroll
+        for (int ct = 0; ct < T::CT; ++ct) {
+          mma8_acc_z(dxn[ct], rd[0], bkT[0][ct][0], bkT[0][ct][1]);
+          mma8_acc(dxn[ct], rk[0], bhT[0][ct][0], bhT[0][ct][1]);
+#pragma unroll
+          for (int kd = 1; kd < 4; ++kd) {
+            mma8_acc(dxn[ct], rd[kd], bkT[kd][ct][0], bkT[kd][ct][1]);
+            mma8_acc(dxn[ct], rk[kd], bhT[kd][ct][0], bhT[kd][ct][1]);
+          }
+        }
+#pragma unroll
+        for (int ct = 0; ct < T::CT; ++ct)
+          if (8 * ct + 2 * t < C) {
+            float* p0 = yp_s + ((size_t)h * SP + 16 * s + g) * T::YS + 8 * ct + 2 * t;
+            *reinterpret_cast<float2*>(p0) = make_float2(dxn[ct][0], dxn[ct][1]);
+            *reinterpret_cast<float2*>(p0 + 8 * T::YS) = make_float2(dxn[ct][2], dxn[ct][3]);
+          }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        uint32_t Bxn[T::CT][2];
+        load_bT<C>(xnT_s, s, j, g, t, Bxn);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          uint32_t Ak[4];
+          load_At(scrK, mt, j, g, t, Ak);
+#pragma unroll
+          for (int ct = 0; ct < T::CT; ++ct) mma8(dwk[mt][ct], Ak[0], Ak[1], Ak[2], Ak[3], Bxn[ct][0], Bxn[ct][1]);
+        }
+      }
+      __syncwarp();
     }
     __syncthreads();
-    if (j < TP && n0 + j < n_end) {
-      const int n = n0 + j;
-      float inv = inv_s[j];
+    {  // thread j = position: RMSNorm_pre backward + residual gradient
+      const int j = threadIdx.x, n = n0 + j;
+      const bool ok = n < n_end;
+      const float inv = inv_s[j];
       float uh[C], duh[C];
       float dot = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        size_t idx = ((size_t)r * C + c) * a.L + n;
-        float dxn = yp_s[(0 * TP + j) * C + c] + yp_s[(1 * TP + j) * C + c] + yp_s[(2 * TP + j) * C + c] +
-                    yp_s[(3 * TP + j) * C + c] + __ldg(a.dxnq + idx);
-        float xv = __ldg(a.x + idx);
+        const size_t idx = ((size_t)r * C + c) * a.L + n;
+        const float dxn = ok ? yp_s[(0 * SP + j) * T::YS + c] + yp_s[(1 * SP + j) * T::YS + c] +
+                                   yp_s[(2 * SP + j) * T::YS + c] + yp_s[(3 * SP + j) * T::YS + c] + __ldg(a.dxnq + idx)
+                             : 0.f;
+        const float xv = ok ? __ldg(a.x + idx) : 0.f;
         uh[c] = xv * inv;
-        acc_s[j * C + c] += dxn * uh[c] * sqrtC;
+        const float dgc = warp_sum(dxn * uh[c] * sqrtC);
+        if (lane == 0) atomicAdd(acc_s + c, dgc);
         duh[c] = dxn * a.g_pre[c] * sqrtC;
         dot = fmaf(duh[c], uh[c], dot);
       }
-      // note: inv = 1/max(norm, eps); norm > eps <=> inv < 1e12
-      const bool big = inv < 1e12f;
+      if (ok) {
+        const bool big = inv < 1e12f;
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        size_t idx = ((size_t)r * C + c) * a.L + n;
-        float d = big ? (duh[c] - uh[c] * dot) * inv : duh[c] * inv;
-        a.dx[idx] = __ldg(a.dres + idx) + d;
+        for (int c = 0; c < C; ++c) {
+          const size_t idx = ((size_t)r * C + c) * a.L + n;
+          const float d = big ? (duh[c] - uh[c] * dot) * inv : duh[c] * inv;
+          a.dx[idx] = __ldg(a.dres + idx) + d;
+        }
       }
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    atomicAdd(a.dwqkv + (size_t)(kHD + j) * C + c, dwk[c]);
-    atomicAdd(a.dwqkv + (size_t)(2 * kHD + j) * C + c, dwv[c]);
-  }
-  if (j < 32) {
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      float s1 = warp_sum(acc_s[j * C + c]);
-      if (j == 0) atomicAdd(a.dg_pre + c, s1);
-    }
-  }
+    for (int ct = 0; ct < T::CT; ++ct)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = h * 32 + 16 * mt + g + 8 * (i >> 1), c = 8 * ct + 2 * t + (i & 1);
+        if (c < C) atomicAdd(a.dwqkv + (size_t)(kHD + d) * C + c, dwk[mt][ct][i]);
+      }
+  __syncthreads();
+  if (threadIdx.x < C) atomicAdd(a.dg_pre + threadIdx.x, acc_s[threadIdx.x]);
 }
 
-void la_combine_launch(const LAArgs& a, cudaStream_t st) { la_combine_kernel<<<(unsigned)a.R, 128, 0, st>>>(a); }
-void la_bwd_combine_launch(const LAArgs& a, cudaStream_t st) { la_bwd_combine_kernel<<<(unsigned)a.R, 128, 0, st>>>(a); }
-
 template <int C>
-static int la_fwd_launch(const LAArgs& a, cudaStream_t st) {
+static int la_fwd(const LAArgs& a, cudaStream_t st) {
+  using T = TC<C>;
   dim3 grid((unsigned)a.nchunk, (unsigned)a.R);
   la_stats_kernel<C><<<grid, 128, 0, st>>>(a);
   DQ_LAUNCH_CHECK();
-  la_combine_kernel<<<(unsigned)a.R, 128, 0, st>>>(a);
+  la_combine_kernel<C><<<(unsigned)a.R, 128, 0, st>>>(a);
   DQ_LAUNCH_CHECK();
-  {
-    size_t smem = sizeof(float) * (TP * C + 2 * TP * LDS_ + C * kHD + 4 * TP * C);
-    cudaFuncSetAttribute(la_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    la_out_kernel<C><<<grid, 128, smem, st>>>(a);
-  }
+  size_t smem = sizeof(float) * (SP * T::XS + 4 * SP * T::YS);
+  cudaFuncSetAttribute(la_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  la_out_kernel<C><<<grid, 128, smem, st>>>(a);
   DQ_LAUNCH_CHECK();
   return 0;
 }
+
 template <int C>
-static int la_bwd_launch(const LAArgs& a, cudaStream_t st) {
+static int la_bwd(const LAArgs& a, cudaStream_t st) {
+  using T = TC<C>;
   dim3 grid((unsigned)a.nchunk, (unsigned)a.R);
   {
-    size_t smem = sizeof(float) * (2 * TP * C + 2 * TP * LDS_ + kHD * C + 4 * TP * C + TP * 4 + TP * 2 * C);
+    size_t smem = sizeof(float) * (2 * SP * T::XS + 2 * T::CP * XT + 4 * SP * T::YS + 4 * 2 * 16 * RS + 2 * C);
     cudaFuncSetAttribute(la_bwd_q_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     la_bwd_q_kernel<C><<<grid, 128, smem, st>>>(a);
+    DQ_LAUNCH_CHECK();
   }
-  DQ_LAUNCH_CHECK();
-  la_bwd_combine_kernel<<<(unsigned)a.R, 128, 0, st>>>(a);
-  DQ_LAUNCH_CHECK();
   {
-    size_t smem = sizeof(float) * (TP * C + 2 * TP * LDS_ + 2 * kHD * C + 4 * TP * C + TP + TP * C);
+    constexpr int kRows = 8;
+    size_t smem = sizeof(float) * (2 * kHD * 33 + 2 * kHD * (C + 1));
+    cudaFuncSetAttribute(la_bwd_combine_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    la_bwd_combine_kernel<C><<<(unsigned)((a.R + kRows - 1) / kRows), 128, smem, st>>>(a, kRows);
+    DQ_LAUNCH_CHECK();
+  }
+  {
+    size_t smem = sizeof(float) * (SP * T::XS + T::CP * XT + 4 * SP * T::YS + 4 * 16 * RS + SP + C);
     cudaFuncSetAttribute(la_bwd_kv_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     la_bwd_kv_kernel<C><<<grid, 128, smem, st>>>(a);
+    DQ_LAUNCH_CHECK();
   }
-  DQ_LAUNCH_CHECK();
   return 0;
 }
 
@@ -622,62 +957,55 @@ static int la_bwd_launch(const LAArgs& a, cudaStream_t st) {
 
 using namespace dq;
 
-// DQ_LA_FP32=1 selects the fp32 CUDA-core kernels (kept as an on-device cross-check of the tensor-core kernels)
-static bool la_use_fp32() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DQ_LA_FP32"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
-
-// chunking policy shared by forward and backward (the Python side sizes `part`/`dpart` from dq_la_nchunk)
+// chunking policy shared by forward and backward (the Python side sizes `part`/`dpart` from dq_la_nchunk):
+// at most ~8192 positions per CTA, chunks of equal size rounded up to whole 128-position sub-tiles
+static int la_nchunk(int L) { return (L + 8191) / 8192; }
 static int la_chunk(int L) {
-  int chunk = 2048;
-  if (L <= 2048) chunk = ((L + TP - 1) / TP) * TP;
-  return chunk;
+  int n = la_nchunk(L);
+  int c = (L + n - 1) / n;
+  return (c + SP - 1) / SP * SP;
 }
 DQ_API int dq_la_nchunk(int L) { int c = la_chunk(L); return (L + c - 1) / c; }
 
 DQ_API int dq_linattn_fwd(const float* x, const float* g_pre, const float* wqkv, const float* wout, const float* bout,
-                          const float* g_out, float* part, float* ctx, float* ms, float* ypre, float* out, int C,
+                          const float* g_out, float* part, float* msm, float* gmat, float* ypre, float* out, int C,
                           int R, int L, void* stream) {
   LAArgs a{};
   a.x = x; a.g_pre = g_pre; a.wqkv = wqkv; a.wout = wout; a.bout = bout; a.g_out = g_out;
-  a.part = part; a.ctx = ctx; a.ms = ms; a.ypre = ypre; a.out = out;
+  a.part = part; a.msm = msm; a.gmat = gmat; a.ypre = ypre; a.out = out;
   a.R = R; a.L = L; a.chunk = la_chunk(L); a.nchunk = (L + a.chunk - 1) / a.chunk;
   cudaStream_t st = (cudaStream_t)stream;
   if (R <= 0 || L <= 0) return 0;
-  if (!la_use_fp32()) return la_fwd_tc_dispatch(a, C, st);
   switch (C) {
-    case 4: return la_fwd_launch<4>(a, st);
-    case 8: return la_fwd_launch<8>(a, st);
-    case 12: return la_fwd_launch<12>(a, st);
-    case 16: return la_fwd_launch<16>(a, st);
-    case 24: return la_fwd_launch<24>(a, st);
-    case 32: return la_fwd_launch<32>(a, st);
+    case 4: return la_fwd<4>(a, st);
+    case 8: return la_fwd<8>(a, st);
+    case 12: return la_fwd<12>(a, st);
+    case 16: return la_fwd<16>(a, st);
+    case 24: return la_fwd<24>(a, st);
+    case 32: return la_fwd<32>(a, st);
     default: return -3;
   }
 }
 
-DQ_API int dq_linattn_bwd(const float* x, const float* dres, const float* ypre, const float* ctx, const float* ms,
+DQ_API int dq_linattn_bwd(const float* x, const float* dres, const float* ypre, const float* msm, const float* gmat,
                           const float* g_pre, const float* wqkv, const float* wout, const float* g_out, float* dxnq,
-                          float* dpart, float* dctx, float* sd, float* dx, float* dwqkv, float* dwout, float* dbout,
+                          float* dpart, float* hmat, float* sd, float* dx, float* dwqkv, float* dwout, float* dbout,
                           float* dg_out, float* dg_pre, int C, int R, int L, void* stream) {
   LAArgs a{};
-  a.x = x; a.dres = dres; a.ypre = const_cast<float*>(ypre); a.ctx = const_cast<float*>(ctx);
-  a.ms = const_cast<float*>(ms); a.g_pre = g_pre; a.wqkv = wqkv; a.wout = wout; a.g_out = g_out;
-  a.dxnq = dxnq; a.dpart = dpart; a.dctx = dctx; a.sd = sd; a.dx = dx; a.dwqkv = dwqkv; a.dwout = dwout;
-  a.dbout = dbout; a.dg_out = dg_out; a.dg_pre = dg_pre;
+  a.x = x; a.dres = dres; a.ypre = const_cast<float*>(ypre); a.msm = const_cast<float*>(msm);
+  a.gmat = const_cast<float*>(gmat); a.g_pre = g_pre; a.wqkv = wqkv; a.wout = wout; a.g_out = g_out;
+  a.dxnq = dxnq; a.dpart = dpart; a.hmat = hmat; a.sd = sd; a.dx = dx;
+  a.dwqkv = dwqkv; a.dwout = dwout; a.dbout = dbout; a.dg_out = dg_out; a.dg_pre = dg_pre;
   a.R = R; a.L = L; a.chunk = la_chunk(L); a.nchunk = (L + a.chunk - 1) / a.chunk;
   cudaStream_t st = (cudaStream_t)stream;
   if (R <= 0 || L <= 0) return 0;
-  if (!la_use_fp32()) return la_bwd_tc_dispatch(a, C, st);
   switch (C) {
-    case 4: return la_bwd_launch<4>(a, st);
-    case 8: return la_bwd_launch<8>(a, st);
-    case 12: return la_bwd_launch<12>(a, st);
-    case 16: return la_bwd_launch<16>(a, st);
-    case 24: return la_bwd_launch<24>(a, st);
-    case 32: return la_bwd_launch<32>(a, st);
+    case 4: return la_bwd<4>(a, st);
+    case 8: return la_bwd<8>(a, st);
+    case 12: return la_bwd<12>(a, st);
+    case 16: return la_bwd<16>(a, st);
+    case 24: return la_bwd<24>(a, st);
+    case 32: return la_bwd<32>(a, st);
     default: return -3;
   }
 }

@@ -457,28 +457,30 @@ class UNet1d(nn.Module):
     def _la_fwd(self, pre, x, save):
         R, C, L = x.shape
         nch = N.la_nchunk(L)
-        part = self._empty(R, nch, HD, 34)
-        ctx = self._empty(R, HD, 32)
-        ms = self._empty(R, HD, 2)
+        cp = _ceil8(C)
+        part = self._empty(R, nch, HD, 2 + cp)
+        msm = self._empty(R, HD, 2 + cp)   # per (row, head*32+d): max, sum, Ms[d][c] = sum_n softmax_L(k)[d,n] xn[c,n]
+        gmat = self._empty(R, C, HD)       # G[c'][head*32+d] = sum_e Wout[c'][e] ctx[d][e]
         ypre = self._empty(R, C, L) if save else None
         out = self._empty(R, C, L)
         N.call("dq_linattn_fwd", x, self._w(pre + ".fn.norm.g"), self._w(pre + ".fn.fn.to_qkv.weight"),
                self._w(pre + ".fn.fn.to_out.0.weight"), self._w(pre + ".fn.fn.to_out.0.bias"),
-               self._w(pre + ".fn.fn.to_out.1.g"), part, ctx, ms, ypre, out, C, R, L)
-        return out, (x, ypre, ctx, ms)
+               self._w(pre + ".fn.fn.to_out.1.g"), part, msm, gmat, ypre, out, C, R, L)
+        return out, (x, ypre, msm, gmat)
 
     def _la_bwd(self, pre, saved, dres):
-        x, ypre, ctx, ms = saved
+        x, ypre, msm, gmat = saved
         R, C, L = x.shape
         nch = N.la_nchunk(L)
+        cp = _ceil8(C)
         dxnq = self._empty(R, C, L)
-        dpart = self._empty(R, nch, HD, 32)
-        dctx = self._empty(R, HD, 32)
+        dpart = self._empty(R, nch, HD, cp)
+        hmat = self._empty(R, HD, cp)
         sd = self._empty(R, HD)
         dx = self._empty(R, C, L)
-        N.call("dq_linattn_bwd", x, dres, ypre, ctx, ms, self._w(pre + ".fn.norm.g"),
+        N.call("dq_linattn_bwd", x, dres, ypre, msm, gmat, self._w(pre + ".fn.norm.g"),
                self._w(pre + ".fn.fn.to_qkv.weight"), self._w(pre + ".fn.fn.to_out.0.weight"),
-               self._w(pre + ".fn.fn.to_out.1.g"), dxnq, dpart, dctx, sd, dx,
+               self._w(pre + ".fn.fn.to_out.1.g"), dxnq, dpart, hmat, sd, dx,
                self._gw(pre + ".fn.fn.to_qkv.weight"), self._gw(pre + ".fn.fn.to_out.0.weight"),
                self._gw(pre + ".fn.fn.to_out.0.bias"), self._gw(pre + ".fn.fn.to_out.1.g"),
                self._gw(pre + ".fn.norm.g"), C, R, L)

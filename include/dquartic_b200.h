@@ -56,15 +56,18 @@ int dq_conv1d_bwd_weight(const float* du, const float* x1, int c1, const float* 
 /* gradient of ConditionalScaleShift (unet1d.py:677-678): per-sample sum d*c and sum d. */
 int dq_sample_dot(const float* d, const float* c, float* dscale, float* dshift, int out_stride, long n_per_sample,
                   int n_samples, void* stream);
-/* Residual(PreNorm(LinearAttention)): unet1d.py:473-496, 1017, 1068.  Scratch sizes: part (R, nchunk,128,34),
- * ctx (R,128,32), ms (R,128,2), dpart (R,nchunk,128,32), dctx (R,128,32), sd (R,128); nchunk = dq_la_nchunk(L). */
+/* Residual(PreNorm(LinearAttention)): unet1d.py:473-496, 1017, 1068, restructured so that every per-head 32x32
+ * contraction factors through the C input channels (csrc/linattn.cu).  CP = C rounded up to 8,
+ * nchunk = dq_la_nchunk(L).  Scratch: part (R,nchunk,128,2+CP), dpart (R,nchunk,128,CP), hmat (R,128,CP),
+ * sd (R,128), dxnq (R,C,L).  Saved by forward for backward: msm (R,128,2+CP) = [max, sum, Ms], gmat (R,C,128),
+ * ypre (R,C,L). */
 int dq_la_nchunk(int L);
 int dq_linattn_fwd(const float* x, const float* g_pre, const float* wqkv, const float* wout, const float* bout,
-                   const float* g_out, float* part, float* ctx, float* ms, float* ypre, float* out, int C, int R,
+                   const float* g_out, float* part, float* msm, float* gmat, float* ypre, float* out, int C, int R,
                    int L, void* stream);
-int dq_linattn_bwd(const float* x, const float* dres, const float* ypre, const float* ctx, const float* ms,
+int dq_linattn_bwd(const float* x, const float* dres, const float* ypre, const float* msm, const float* gmat,
                    const float* g_pre, const float* wqkv, const float* wout, const float* g_out, float* dxnq,
-                   float* dpart, float* dctx, float* sd, float* dx, float* dwqkv, float* dwout, float* dbout,
+                   float* dpart, float* hmat, float* sd, float* dx, float* dwqkv, float* dwout, float* dbout,
                    float* dg_out, float* dg_pre, int C, int R, int L, void* stream);
 
 /* ---- time embedding and per-sample linears (unet1d.py:211-218, 958-960, 292-296, 664, 535) ------------ */

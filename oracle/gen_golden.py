@@ -275,15 +275,21 @@ def gen_data():
     print("data ok", out["pairs520"][:4].tolist(), pairs_small[:3])
 
 
-def gen_curve():
-    """200 optimizer steps at a shrunken shape, batch 2, batched-oracle semantics on the REFERENCE modules."""
-    cfg = dict(TINY, downsample_dim=128)
-    b, rt, mz, steps = 2, 6, 128, 200
+def _curve_run(cfg, b, rt, mz, steps, lr, perturb=0.0):
+    """One reference training trajectory (batched-oracle semantics on the REFERENCE modules).  `perturb` > 0
+    multiplies every initial weight by (1 + perturb * N(0,1)): the control run that measures how far the
+    REFERENCE ITSELF moves under an fp32-rounding-sized change of its inputs."""
     m, _ = ref_model(cfg, seed=3)
+    if perturb > 0:
+        gp = torch.Generator().manual_seed(99)
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.requires_grad:
+                    p.mul_(1 + perturb * torch.randn(p.shape, generator=gp))
     m.train()
     ddim = DDIMDiffusionModel(model_class=m, num_timesteps=1000, device="cpu")
     ms2, ms1 = synth_pool(12, rt, mz, seed=11, density=0.3)
-    opt = torch.optim.AdamW(m.parameters(), lr=2e-3)
+    opt = torch.optim.AdamW(m.parameters(), lr=lr)
     rng = random.Random(4321)
     used = set()
     g = torch.Generator().manual_seed(777)
@@ -323,11 +329,28 @@ def gen_curve():
         opt.step()
         losses.append(float(np.mean(step_losses)))
         if s % 50 == 0:
-            print("curve step", s, losses[-1])
-    np.savez_compressed(os.path.join(GOLD, "curve_tiny.npz"), losses=np.array(losses, np.float32),
-                        pairs=np.array(pair_log, np.int64), t=np.array(t_log, np.int64),
-                        cfg=json.dumps(cfg), shape=np.array([b, rt, mz, steps]))
-    print("curve ok", losses[0], losses[-1])
+            print("curve step", s, losses[-1], flush=True)
+    return np.array(losses, np.float32), np.array(pair_log, np.int64), np.array(t_log, np.int64)
+
+
+def gen_curve():
+    """200 optimizer steps at a shrunken shape, batch 2: (i) at the reference's shipped learning rate 1e-5
+    (dquartic_train_config.json:15), (ii) at 5e-4 where the loss falls from 1.3 to ~0.5, and for each a CONTROL
+    trajectory of the unmodified reference with its initial weights perturbed by 1e-6 relative (a few fp32 ulps):
+    the control bounds how closely ANY second implementation can be expected to follow the curve."""
+    cfg = dict(TINY, downsample_dim=128)
+    b, rt, mz, steps = 2, 6, 128, 200
+    out = {}
+    for tag, lr in (("cfg_lr", 1e-5), ("", 5e-4)):
+        losses, pairs, ts = _curve_run(cfg, b, rt, mz, steps, lr)
+        ctrl, _, _ = _curve_run(cfg, b, rt, mz, steps, lr, perturb=1e-6)
+        sfx = "_" + tag if tag else ""
+        out["losses" + sfx] = losses
+        out["losses_ctrl" + sfx] = ctrl
+        out["lr" + sfx] = np.float64(lr)
+        print("curve", lr, losses[0], losses[-1], "ctrl max rel dev", float(np.max(np.abs(ctrl - losses) / losses)))
+    np.savez_compressed(os.path.join(GOLD, "curve_tiny.npz"), pairs=pairs, t=ts,
+                        cfg=json.dumps(cfg), shape=np.array([b, rt, mz, steps]), **out)
 
 
 if __name__ == "__main__":
