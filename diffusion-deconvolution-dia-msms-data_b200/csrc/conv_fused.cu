@@ -1,0 +1,826 @@
+// Fused backward of one stride-1 Conv1d (K = 1 or 3, "same" padding) of the down/up path together with the
+// backward of its Block epilogue (reference /root/reference/dquartic/model/unet1d.py: Block.forward 248-268,
+// RMSNorm 140, ResnetBlock.forward 302-323 incl. the 1x1 res_conv 300/323):
+//
+//      du  = d(RMSNorm * (scale+1) + shift -> SiLU)^T dy            (pointwise over channels; skipped if u == null)
+//      dx  = conv_transpose(du, W) (+ dadd)                         (dual destination = backward of the skip concat)
+//      dW += du (x) x,  db += sum du,  dg / d scale / d shift += ...
+//
+// One pass over HBM: dy, u and x are read once, dx is written once (the three-kernel version wrote du and re-read
+// it, and re-read du / x once per 4x4 channel tile of dW).  A persistent CTA walks a contiguous range of
+// (row, 128*P-position) tiles; per tile
+//   phase 1: thread-per-position epilogue backward -> du tile (+1 halo each side) and x tile into shared memory
+//   phase 2: dx for the thread's positions from the du tile (taps from shared memory, weights broadcast)
+//   phase 3: dW as a small GEMM over the tile: thread (ci, segment) keeps dW[:, ci, :] in registers for the whole
+//            CTA lifetime, streaming du / x rows with 128-bit shared loads
+// and the parameter gradients leave the CTA once (shared-memory combine, then one global atomic per value).
+// HBM-bound: algorithmic bytes per position = 4 * (2 * COUT + 2 * cin) (+ 4 * c1 with dadd / accumulate).
+#include <stdlib.h>
+#include "common.cuh"
+
+namespace dq {
+
+struct ConvBwdFusedArgs {
+  const float* dy;    // (R, COUT, L) gradient of the block output
+  const float* u;     // (R, COUT, L) saved pre-norm conv output, or null: plain conv (du = dy)
+  const float* g;     // (COUT) RMSNorm gain or null
+  const float* ss;    // per-sample scale/shift (scale = ss[s*ss_stride + c], shift = [.. + COUT + c]) or null
+  const float* x1;    // (R, c1, L) forward source 1
+  const float* x2;    // (R, c2, L) forward source 2 or null
+  const float* w;     // (COUT, c1+c2, K)
+  const float* dadd;  // optional (R, c1, L): added to dx1 (identity-skip gradient)
+  float* dx1;         // (R, c1, L) or null
+  float* dx2;         // (R, c2, L) or null
+  float* dw;          // (COUT, cin, K) accumulated
+  float* db;          // (COUT) accumulated or null
+  float* dg;          // (COUT) accumulated or null
+  float* dss;         // same layout as ss, accumulated, or null
+  int c1, c2, R, L, rows_per_sample, ss_stride, act, acc1, acc2, tiles_per_row, total_tiles, tiles_per_cta;
+};
+
+// VEC == 4: thread t owns positions 4t .. 4t+3 of the tile (128-bit global accesses; needs L % 4 == 0)
+// VEC == 1: thread t owns positions t + 128 i (coalesced scalar accesses)
+template <int COUT, int K, int P, int VEC>
+__global__ void __launch_bounds__(128) conv_bwd_fused_kernel(ConvBwdFusedArgs a) {
+  constexpr int TL = 128 * P;
+  constexpr int DS = TL + 4;          // row stride of the smem tiles (= 4 mod 32); position p lives at index p + 4
+  constexpr int H = (K - 1) / 2;      // halo
+  constexpr int NPA = 4 * COUT;       // per-thread phase-1 accumulators: dg, dscale, dshift, db
+  static_assert(VEC == 1 || (VEC == 4 && P == 4), "vector mode needs 4 positions per thread");
+  extern __shared__ float4 dyn_smem4[];
+  float* du_s = reinterpret_cast<float*>(dyn_smem4);   // COUT * DS + 8
+  const int cin = a.c1 + a.c2;
+  float* x_s = du_s + COUT * DS + 8;                   // cin * DS + 8
+  float* w_s = x_s + cin * DS + 8;                     // COUT * cin * 4   [(co*cin + ci)*4 + k]
+  float* dw_s = w_s + COUT * cin * 4;                  // COUT * cin * K   combine buffer
+  float* red = dw_s + COUT * cin * K;                  // 4 * NPA
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < COUT * cin * 4; i += 128) {
+    const int k = i & 3, pc = i >> 2;
+    w_s[i] = (k < K) ? a.w[(size_t)pc * K + k] : 0.f;
+  }
+  for (int i = tid; i < COUT * cin * K; i += 128) dw_s[i] = 0.f;
+
+  // phase-3 role: input channel ci, position segment seg
+  const int nseg = max(1, 128 / cin);
+  const int ci3 = tid % cin, seg = tid / cin;
+  const bool p3_active = seg < nseg && tid < nseg * cin;
+  const int SL = ((TL + nseg - 1) / nseg + 3) & ~3;
+  const int q_begin = seg * SL, q_end = min(TL, q_begin + SL);
+  float dwacc[COUT][K];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co)
+#pragma unroll
+    for (int k = 0; k < K; ++k) dwacc[co][k] = 0.f;
+  float pacc[NPA];
+#pragma unroll
+  for (int i = 0; i < NPA; ++i) pacc[i] = 0.f;
+
+  const float sqrtC = sqrtf((float)COUT);
+  const int t_begin = blockIdx.x * a.tiles_per_cta, t_end = min(a.total_tiles, t_begin + a.tiles_per_cta);
+  int cur_sample = -1;
+
+  auto flush_sample = [&](int sample) {   // per-sample scale/shift gradients leave the CTA when the sample changes
+    float v[2 * COUT];
+#pragma unroll
+    for (int c = 0; c < 2 * COUT; ++c) { v[c] = pacc[COUT + c]; pacc[COUT + c] = 0.f; }
+    const float tot = block_reduce_vec<2 * COUT>(v, red);
+    if (a.dss && a.ss && tid < 2 * COUT) atomicAdd(a.dss + (size_t)sample * a.ss_stride + tid, tot);
+  };
+
+  for (int tile = t_begin; tile < t_end; ++tile) {
+    const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
+    const int sample = r / a.rows_per_sample;
+    if (sample != cur_sample) {
+      if (cur_sample >= 0 && a.u) flush_sample(cur_sample);
+      cur_sample = sample;
+    }
+    __syncthreads();  // previous tile's phases 2/3 are done with the tiles (also covers the w_s / dw_s init)
+
+    // ---------------------------------------------------------------- phase 1: du tile and x tile
+    {
+      float gl[COUT], scale1[COUT], shift[COUT];
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        gl[c] = a.g ? a.g[c] : 1.f;
+        scale1[c] = a.ss ? a.ss[(size_t)sample * a.ss_stride + c] + 1.f : 1.f;
+        shift[c] = a.ss ? a.ss[(size_t)sample * a.ss_stride + COUT + c] : 0.f;
+      }
+      // P own positions, then (threads 0 / 1 only) the left / right halo position
+      auto du_at = [&](const float (&dyv)[COUT], const float (&uvin)[COUT], float (&duv)[COUT], bool accumulate) {
+        if (!a.u) {
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) { duv[c] = dyv[c]; if (accumulate) pacc[3 * COUT + c] += dyv[c]; }
+          return;
+        }
+        float uv[COUT];
+        float s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) { uv[c] = uvin[c]; s2 = fmaf(uv[c], uv[c], s2); }
+        const float nrm = sqrtf(s2);
+        const float inv = a.g ? 1.f / fmaxf(nrm, 1e-12f) : 1.f;
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          const float uh = uv[c] * inv;
+          const float n = a.g ? uh * gl[c] * sqrtC : uv[c];
+          const float z = fmaf(n, scale1[c], shift[c]);
+          const float d = dyv[c] * act_bwd(z, a.act);
+          const float dn = d * scale1[c];
+          if (accumulate) {
+            pacc[c] += dn * uh * sqrtC;        // d g
+            pacc[COUT + c] += d * n;           // d scale
+            pacc[2 * COUT + c] += d;           // d shift
+          }
+          const float duh = a.g ? dn * gl[c] * sqrtC : dn;
+          duv[c] = duh;
+          dot = fmaf(duh, uh, dot);
+          uv[c] = uh;
+        }
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          float d;
+          if (!a.g) d = duv[c];
+          else if (nrm > 1e-12f) d = (duv[c] - uv[c] * dot) * inv;
+          else d = duv[c] * inv;
+          duv[c] = d;
+          if (accumulate) pacc[3 * COUT + c] += d;   // d bias
+        }
+      };
+      const size_t rowbase = (size_t)r * COUT * a.L;
+      if (VEC == 4) {
+        const int l = tl0 + 4 * tid;
+        const bool ok = l < a.L;
+        float4 dy4[COUT], u4[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          dy4[c] = ok ? __ldg(reinterpret_cast<const float4*>(a.dy + rowbase + (size_t)c * a.L + l)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          u4[c] = (ok && a.u) ? __ldg(reinterpret_cast<const float4*>(a.u + rowbase + (size_t)c * a.L + l)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float o[4][COUT];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float dyv[COUT], uv[COUT];
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) {
+            dyv[c] = i == 0 ? dy4[c].x : i == 1 ? dy4[c].y : i == 2 ? dy4[c].z : dy4[c].w;
+            uv[c] = i == 0 ? u4[c].x : i == 1 ? u4[c].y : i == 2 ? u4[c].z : u4[c].w;
+          }
+          du_at(dyv, uv, o[i], ok);
+          if (!ok) {
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) o[i][c] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < COUT; ++c)
+          *reinterpret_cast<float4*>(du_s + c * DS + 4 + 4 * tid) = make_float4(o[0][c], o[1][c], o[2][c], o[3][c]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+          const int l = tl0 + tid + 128 * i;
+          const bool ok = l < a.L;
+          float dyv[COUT], uv[COUT], o[COUT];
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) {
+            dyv[c] = ok ? __ldg(a.dy + rowbase + (size_t)c * a.L + l) : 0.f;
+            uv[c] = (ok && a.u) ? __ldg(a.u + rowbase + (size_t)c * a.L + l) : 0.f;
+          }
+          du_at(dyv, uv, o, ok);
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) du_s[c * DS + 4 + tid + 128 * i] = ok ? o[c] : 0.f;
+        }
+      }
+      if (H > 0 && tid < 2) {  // halo positions tl0 - 1 (thread 0) and tl0 + TL (thread 1): no accumulation
+        const int l = tid == 0 ? tl0 - 1 : tl0 + TL;
+        const bool ok = l >= 0 && l < a.L;
+        float dyv[COUT], uv[COUT], o[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          dyv[c] = ok ? __ldg(a.dy + rowbase + (size_t)c * a.L + l) : 0.f;
+          uv[c] = (ok && a.u) ? __ldg(a.u + rowbase + (size_t)c * a.L + l) : 0.f;
+        }
+        du_at(dyv, uv, o, false);
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) du_s[c * DS + (tid == 0 ? 3 : TL + 4)] = ok ? o[c] : 0.f;
+      }
+      // x tile
+      for (int ci = 0; ci < cin; ++ci) {
+        const float* xr = (ci < a.c1) ? a.x1 + ((size_t)r * a.c1 + ci) * a.L : a.x2 + ((size_t)r * a.c2 + (ci - a.c1)) * a.L;
+        if (VEC == 4) {
+          const int l = tl0 + 4 * tid;
+          *reinterpret_cast<float4*>(x_s + ci * DS + 4 + 4 * tid) =
+              (l < a.L) ? __ldg(reinterpret_cast<const float4*>(xr + l)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+          for (int i = 0; i < P; ++i) {
+            const int l = tl0 + tid + 128 * i;
+            x_s[ci * DS + 4 + tid + 128 * i] = (l < a.L) ? __ldg(xr + l) : 0.f;
+          }
+        }
+      }
+      if (H > 0) {
+        for (int i = tid; i < 2 * cin; i += 128) {
+          const int ci = i >> 1, right = i & 1;
+          const int l = right ? tl0 + TL : tl0 - 1;
+          const float* xr = (ci < a.c1) ? a.x1 + ((size_t)r * a.c1 + ci) * a.L : a.x2 + ((size_t)r * a.c2 + (ci - a.c1)) * a.L;
+          x_s[ci * DS + (right ? TL + 4 : 3)] = (l >= 0 && l < a.L) ? __ldg(xr + l) : 0.f;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- phase 2: dx for the thread's positions
+    if (a.dx1 || a.dx2) {
+      for (int cb = 0; cb < cin; cb += 4) {
+        float acc[4][P];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < P; ++i) acc[j][i] = 0.f;
+#pragma unroll 2
+        for (int co = 0; co < COUT; ++co) {
+          float dn[P][K];   // dn[i][k] = du[co][pos_i + H - k]
+          if (VEC == 4) {
+            const float4 m = *reinterpret_cast<const float4*>(du_s + co * DS + 4 + 4 * tid);
+            if (K == 3) {
+              const float lft = du_s[co * DS + 3 + 4 * tid], rgt = du_s[co * DS + 8 + 4 * tid];
+              const float d6[6] = {lft, m.x, m.y, m.z, m.w, rgt};
+#pragma unroll
+              for (int i = 0; i < P; ++i)
+#pragma unroll
+                for (int k = 0; k < K; ++k) dn[i][k] = d6[i + 2 - k];
+            } else {
+              dn[0][0] = m.x; dn[1][0] = m.y; dn[2][0] = m.z; dn[3][0] = m.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < P; ++i)
+#pragma unroll
+              for (int k = 0; k < K; ++k) dn[i][k] = du_s[co * DS + 4 + tid + 128 * i + H - k];
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (cb + j < cin) {
+              const float4 w4 = *reinterpret_cast<const float4*>(w_s + (co * cin + cb + j) * 4);
+              const float wk[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+              for (int i = 0; i < P; ++i)
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[j][i] = fmaf(dn[i][k], wk[k], acc[j][i]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ci = cb + j;
+          if (ci >= cin) continue;
+          float* dst;
+          int accf;
+          const float* add = nullptr;
+          if (ci < a.c1) {
+            dst = a.dx1 ? a.dx1 + ((size_t)r * a.c1 + ci) * a.L : nullptr;
+            accf = a.acc1;
+            if (a.dadd) add = a.dadd + ((size_t)r * a.c1 + ci) * a.L;
+          } else {
+            dst = a.dx2 ? a.dx2 + ((size_t)r * a.c2 + (ci - a.c1)) * a.L : nullptr;
+            accf = a.acc2;
+          }
+          if (!dst) continue;
+          if (VEC == 4) {
+            const int l = tl0 + 4 * tid;
+            if (l < a.L) {
+              float4 v = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+              if (add) { const float4 q = __ldg(reinterpret_cast<const float4*>(add + l)); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+              if (accf) { const float4 q = *reinterpret_cast<const float4*>(dst + l); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+              *reinterpret_cast<float4*>(dst + l) = v;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+              const int l = tl0 + tid + 128 * i;
+              if (l < a.L) {
+                float v = acc[j][i];
+                if (add) v += __ldg(add + l);
+                if (accf) v += dst[l];
+                dst[l] = v;
+              }
+            }
+          }
+        }
+      }
+    }
+
+    // ---------------------------------------------------------------- phase 3: dW[:, ci3, :] over this thread's segment
+    if (p3_active) {
+      const float* xr = x_s + ci3 * DS + 4;
+      for (int q = q_begin; q < q_end; q += 4) {
+        const float4 xm = *reinterpret_cast<const float4*>(xr + q);
+        float x6[6] = {0.f, xm.x, xm.y, xm.z, xm.w, 0.f};
+        if (K == 3) { x6[0] = xr[q - 1]; x6[5] = xr[q + 4]; }
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+          const float4 d4 = *reinterpret_cast<const float4*>(du_s + co * DS + 4 + q);
+          const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dwacc[co][k] = fmaf(dd[i], x6[i + k + 1 - H], dwacc[co][k]);
+        }
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ leave: parameter gradients
+  if (cur_sample >= 0 && a.u) flush_sample(cur_sample);
+  if (p3_active) {
+#pragma unroll
+    for (int co = 0; co < COUT; ++co)
+#pragma unroll
+      for (int k = 0; k < K; ++k) atomicAdd(dw_s + (co * cin + ci3) * K + k, dwacc[co][k]);
+  }
+  {
+    float v[2 * COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) { v[c] = pacc[c]; v[COUT + c] = pacc[3 * COUT + c]; }
+    const float tot = block_reduce_vec<2 * COUT>(v, red);   // includes the __syncthreads that publishes dw_s
+    if (tid < COUT) { if (a.dg && a.g && a.u) atomicAdd(a.dg + tid, tot); }
+    else if (tid < 2 * COUT) { if (a.db) atomicAdd(a.db + tid - COUT, tot); }
+  }
+  for (int i = tid; i < COUT * cin * K; i += 128) atomicAdd(a.dw + i, dw_s[i]);
+}
+
+// =====================================================================================================================
+// Pipelined variant (L % 4 == 0): the raw dy / u / x rows of a tile are brought into shared memory by 1-D bulk
+// async copies (cp.async.bulk, the TMA engine) that complete on an mbarrier, two tiles deep, so the HBM latency of
+// tile t+1 / t+2 hides behind the arithmetic of tile t and no thread spends issue slots on global address math.
+// A row of a stage holds positions [tl0-4, tl0+TL+4) at indices [0, TL+8); row stride TS = TL + 36 (= 4 mod 32).
+__device__ __forceinline__ uint32_t cf_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cf_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void cf_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cf_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void cf_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ float cf_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float cf_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float cf_rsqrt(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// d SiLU(z) / dz with single-MUFU exp / reciprocal (|rel err| ~ 1e-6)
+__device__ __forceinline__ float cf_dsilu(float z) {
+  const float s = cf_rcp(1.f + cf_ex2(-1.4426950408889634f * z));
+  return s * fmaf(z, 1.f - s, 1.f);
+}
+
+template <int COUT, int K, int P, int NT>
+__global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs a) {
+  constexpr int TL = NT * P;
+  constexpr int TS = TL + 36;
+  constexpr int H = (K - 1) / 2;
+  constexpr int NPA = 4 * COUT;
+  constexpr int NW = NT / 32;
+  static_assert(P == 2 || P == 4, "P");
+  extern __shared__ float4 dyn_smem4[];
+  const int cin = a.c1 + a.c2;
+  const bool has_u = a.u != nullptr;
+  const int rows = (has_u ? 2 * COUT : COUT) + cin;      // dy rows, [u rows], x rows
+  float* stage0 = reinterpret_cast<float*>(dyn_smem4);
+  const int stage_floats = rows * TS;
+  float* du_s = stage0 + 2 * stage_floats;               // COUT * TS
+  float* w_s = du_s + COUT * TS;                         // COUT * cin * 4
+  float* dw_s = w_s + COUT * cin * 4;                    // COUT * cin * K
+  float* red = dw_s + COUT * cin * K;                    // NW * 2 * COUT
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + NW * 2 * COUT + ((NW * 2 * COUT) & 1));
+  const int tid = threadIdx.x;
+  const uint32_t bar0 = cf_smem_u32(bars), bar1 = bar0 + 8;
+
+  if (tid == 0) {
+    cf_mbar_init(bar0, 1);
+    cf_mbar_init(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < COUT * cin * 4; i += NT) {
+    const int k = i & 3, pc = i >> 2;
+    w_s[i] = (k < K) ? a.w[(size_t)pc * K + k] : 0.f;
+  }
+  for (int i = tid; i < COUT * cin * K; i += NT) dw_s[i] = 0.f;
+  __syncthreads();
+
+  const int t_begin = blockIdx.x * a.tiles_per_cta, t_end = min(a.total_tiles, t_begin + a.tiles_per_cta);
+  const int n_tiles = t_end - t_begin;
+
+  // one lane per row issues that row's bulk copy; lane 0 posts the expected byte count first
+  auto issue = [&](int tile, int s) {
+    if (tid < 32) {
+      const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
+      const int l_lo = max(0, tl0 - 4), l_hi = min(a.L, tl0 + TL + 4);
+      const uint32_t bytes = (uint32_t)(l_hi - l_lo) * 4u;
+      const uint32_t bar = s ? bar1 : bar0;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (tid == 0) cf_mbar_expect_tx(bar, bytes * (uint32_t)rows);
+      __syncwarp();
+      float* st = stage0 + s * stage_floats;
+      for (int row = tid; row < rows; row += 32) {
+        const float* src;
+        if (row < COUT) src = a.dy + ((size_t)r * COUT + row) * a.L;
+        else if (has_u && row < 2 * COUT) src = a.u + ((size_t)r * COUT + (row - COUT)) * a.L;
+        else {
+          const int ci = row - (has_u ? 2 * COUT : COUT);
+          src = (ci < a.c1) ? a.x1 + ((size_t)r * a.c1 + ci) * a.L : a.x2 + ((size_t)r * a.c2 + (ci - a.c1)) * a.L;
+        }
+        cf_bulk_g2s(cf_smem_u32(st + row * TS + (l_lo - (tl0 - 4))), src + l_lo, bytes, bar);
+      }
+    }
+  };
+  if (n_tiles > 0) issue(t_begin, 0);
+  if (n_tiles > 1) issue(t_begin + 1, 1);
+
+  // phase-3 role: input channel ci3, position segment seg
+  const int nseg = max(1, NT / cin);
+  const int ci3 = tid % cin, seg = tid / cin;
+  const bool p3_active = tid < nseg * cin;
+  const int SL = ((TL + nseg - 1) / nseg + 3) & ~3;
+  const int q_begin = seg * SL, q_end = min(TL, q_begin + SL);
+  float dwacc[COUT][K];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co)
+#pragma unroll
+    for (int k = 0; k < K; ++k) dwacc[co][k] = 0.f;
+  float pacc[NPA];
+#pragma unroll
+  for (int i = 0; i < NPA; ++i) pacc[i] = 0.f;
+  const float sqrtC = sqrtf((float)COUT);
+  const bool has_g = a.g != nullptr, has_ss = a.ss != nullptr, silu = a.act == 1;
+  int cur_sample = -1;
+
+  auto block_sum2c = [&](float (&v)[2 * COUT]) -> float {   // thread i < 2*COUT returns the block total of v[i]
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < 2 * COUT; ++i) {
+      const float sres = warp_sum(v[i]);
+      if (lane == 0) red[warp * 2 * COUT + i] = sres;
+    }
+    __syncthreads();
+    float out = 0.f;
+    if (tid < 2 * COUT)
+      for (int w = 0; w < NW; ++w) out += red[w * 2 * COUT + tid];
+    __syncthreads();
+    return out;
+  };
+  auto flush_sample = [&](int sample) {
+    float v[2 * COUT];
+#pragma unroll
+    for (int c = 0; c < 2 * COUT; ++c) { v[c] = pacc[COUT + c]; pacc[COUT + c] = 0.f; }
+    const float tot = block_sum2c(v);
+    if (a.dss && has_ss && tid < 2 * COUT) atomicAdd(a.dss + (size_t)sample * a.ss_stride + tid, tot);
+  };
+
+  for (int it = 0; it < n_tiles; ++it) {
+    const int tile = t_begin + it, s = it & 1;
+    const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
+    const int sample = r / a.rows_per_sample;
+    if (sample != cur_sample) {
+      if (cur_sample >= 0 && has_u) flush_sample(cur_sample);
+      cur_sample = sample;
+    }
+    const float* dy_t = stage0 + s * stage_floats;           // [COUT][TS]
+    const float* u_t = dy_t + COUT * TS;                     // [COUT][TS] (if has_u)
+    float* x_t = stage0 + s * stage_floats + (has_u ? 2 * COUT : COUT) * TS;   // [cin][TS]
+    cf_mbar_wait(s ? bar1 : bar0, (uint32_t)((it >> 1) & 1));
+
+    // ---------------------------------------------------------------- phase 1: du tile
+    {
+      float gl[COUT], scale1[COUT], shift[COUT];
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        gl[c] = has_g ? a.g[c] * sqrtC : 1.f;
+        scale1[c] = has_ss ? a.ss[(size_t)sample * a.ss_stride + c] + 1.f : 1.f;
+        shift[c] = has_ss ? a.ss[(size_t)sample * a.ss_stride + COUT + c] : 0.f;
+      }
+      // inputs of non-existent positions are zeroed at load time, which makes every derived quantity exactly 0
+      auto du_at = [&](const float (&dyv)[COUT], const float (&uvin)[COUT], float (&duv)[COUT], bool accumulate) {
+        if (!has_u) {
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) {
+            duv[c] = dyv[c];
+            if (accumulate) pacc[3 * COUT + c] += duv[c];
+          }
+          return;
+        }
+        float uh[COUT];
+        float s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) s2 = fmaf(uvin[c], uvin[c], s2);
+        const bool big = s2 > 1e-24f;                        // ||u|| > 1e-12 (F.normalize eps)
+        const float inv = has_g ? (big ? cf_rsqrt(s2) : 1e12f) : 1.f;
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          uh[c] = uvin[c] * inv;
+          const float n = uh[c] * gl[c];                     // gl already carries sqrt(C) (or 1 without norm)
+          const float z = fmaf(n, scale1[c], shift[c]);
+          const float d = dyv[c] * (silu ? cf_dsilu(z) : act_bwd(z, a.act));
+          const float dn = d * scale1[c];
+          if (accumulate) {
+            pacc[c] += dn * uh[c];                           // d g / sqrt(C)
+            pacc[COUT + c] += d * n;                         // d scale
+            pacc[2 * COUT + c] += d;                         // d shift
+          }
+          duv[c] = dn * gl[c];                               // d u-hat (no norm: plain d u)
+          dot = fmaf(duv[c], uh[c], dot);
+        }
+        if (has_g) {
+          const float k = big ? dot : 0.f;
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) duv[c] = (duv[c] - uh[c] * k) * inv;
+        }
+        if (accumulate) {
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) pacc[3 * COUT + c] += duv[c];   // d bias
+        }
+      };
+      {
+        const int idx = 4 + P * tid;
+        const bool ok = tl0 + P * tid < a.L;
+        float dyv[P][COUT], uv[P][COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          if (P == 4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(dy_t + c * TS + idx);
+            dyv[0][c] = d4.x; dyv[1][c] = d4.y; dyv[2][c] = d4.z; dyv[3][c] = d4.w;
+            if (has_u) {
+              const float4 u4 = *reinterpret_cast<const float4*>(u_t + c * TS + idx);
+              uv[0][c] = u4.x; uv[1][c] = u4.y; uv[2][c] = u4.z; uv[3][c] = u4.w;
+            }
+          } else {
+            const float2 d2 = *reinterpret_cast<const float2*>(dy_t + c * TS + idx);
+            dyv[0][c] = d2.x; dyv[1][c] = d2.y;
+            if (has_u) {
+              const float2 u2 = *reinterpret_cast<const float2*>(u_t + c * TS + idx);
+              uv[0][c] = u2.x; uv[1][c] = u2.y;
+            }
+          }
+        }
+        if (!ok) {
+#pragma unroll
+          for (int i = 0; i < P; ++i)
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) { dyv[i][c] = 0.f; uv[i][c] = 0.f; }
+        }
+        float o[P][COUT];
+#pragma unroll
+        for (int i = 0; i < P; ++i) du_at(dyv[i], uv[i], o[i], true);
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          if (P == 4) *reinterpret_cast<float4*>(du_s + c * TS + idx) = make_float4(o[0][c], o[1][c], o[2][c], o[3][c]);
+          else *reinterpret_cast<float2*>(du_s + c * TS + idx) = make_float2(o[0][c], o[1][c]);
+        }
+      }
+      if (H > 0 && (tid == 0 || tid == NT - 1)) {   // halo positions tl0 - 1 and tl0 + TL (no accumulation)
+        const int idx = tid == 0 ? 3 : TL + 4;
+        const int l = tl0 - 4 + idx;
+        const bool ok = l >= 0 && l < a.L;
+        float dyv[COUT], uv[COUT], o[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          dyv[c] = ok ? dy_t[c * TS + idx] : 0.f;
+          uv[c] = (ok && has_u) ? u_t[c * TS + idx] : 0.f;
+        }
+        du_at(dyv, uv, o, false);
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) du_s[c * TS + idx] = o[c];
+      }
+      // x rows: exact zeros at the two out-of-range neighbours a valid du can touch (row start / row end)
+      if (tid < cin) {
+        if (tl0 == 0) x_t[tid * TS + 3] = 0.f;
+        if (a.L <= tl0 + TL) x_t[tid * TS + (a.L - tl0 + 4)] = 0.f;
+      }
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- phase 2: dx for the thread's positions
+    if (a.dx1 || a.dx2) {
+      const int l = tl0 + P * tid;
+      const bool ok = l < a.L;
+      for (int cb = 0; cb < cin; cb += 4) {
+        float acc[4][P];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < P; ++i) acc[j][i] = 0.f;
+#pragma unroll 4
+        for (int co = 0; co < COUT; ++co) {
+          float dwin[P + 2];   // du[co][pos - 1 .. pos + P]
+          const float* dr = du_s + co * TS + 4 + P * tid;
+          if (P == 4) { const float4 m = *reinterpret_cast<const float4*>(dr); dwin[1] = m.x; dwin[2] = m.y; dwin[3] = m.z; dwin[4] = m.w; }
+          else { const float2 m = *reinterpret_cast<const float2*>(dr); dwin[1] = m.x; dwin[2] = m.y; }
+          if (K == 3) { dwin[0] = dr[-1]; dwin[P + 1] = dr[P]; }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (cb + j < cin) {
+              const float4 w4 = *reinterpret_cast<const float4*>(w_s + (co * cin + cb + j) * 4);
+              const float wk[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+              for (int i = 0; i < P; ++i)
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[j][i] = fmaf(dwin[i + 1 + H - k], wk[k], acc[j][i]);
+            }
+          }
+        }
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ci = cb + j;
+            if (ci >= cin) continue;
+            float* dst;
+            int accf;
+            const float* add = nullptr;
+            if (ci < a.c1) {
+              dst = a.dx1 ? a.dx1 + ((size_t)r * a.c1 + ci) * a.L : nullptr;
+              accf = a.acc1;
+              if (a.dadd) add = a.dadd + ((size_t)r * a.c1 + ci) * a.L;
+            } else {
+              dst = a.dx2 ? a.dx2 + ((size_t)r * a.c2 + (ci - a.c1)) * a.L : nullptr;
+              accf = a.acc2;
+            }
+            if (!dst) continue;
+            if (P == 4) {
+              float4 v = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+              if (add) { const float4 q = __ldg(reinterpret_cast<const float4*>(add + l)); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+              if (accf) { const float4 q = *reinterpret_cast<const float4*>(dst + l); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+              *reinterpret_cast<float4*>(dst + l) = v;
+            } else {
+              float2 v = make_float2(acc[j][0], acc[j][1]);
+              if (add) { const float2 q = __ldg(reinterpret_cast<const float2*>(add + l)); v.x += q.x; v.y += q.y; }
+              if (accf) { const float2 q = *reinterpret_cast<const float2*>(dst + l); v.x += q.x; v.y += q.y; }
+              *reinterpret_cast<float2*>(dst + l) = v;
+            }
+          }
+        }
+      }
+    }
+
+    // ---------------------------------------------------------------- phase 3: dW[:, ci3, :] over this thread's segment
+    if (p3_active) {
+      const float* xr = x_t + ci3 * TS + 4;
+      for (int q = q_begin; q < q_end; q += 4) {
+        const float4 xm = *reinterpret_cast<const float4*>(xr + q);
+        float x6[6] = {0.f, xm.x, xm.y, xm.z, xm.w, 0.f};
+        if (K == 3) { x6[0] = xr[q - 1]; x6[5] = xr[q + 4]; }
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+          const float4 d4 = *reinterpret_cast<const float4*>(du_s + co * TS + 4 + q);
+          const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dwacc[co][k] = fmaf(dd[i], x6[i + k + 1 - H], dwacc[co][k]);
+        }
+      }
+    }
+    __syncthreads();   // everyone is done with stage s and du_s
+    if (it + 2 < n_tiles) issue(tile + 2, s);
+  }
+
+  // ------------------------------------------------------------------ leave: parameter gradients
+  if (cur_sample >= 0 && has_u) flush_sample(cur_sample);
+  if (p3_active) {
+#pragma unroll
+    for (int co = 0; co < COUT; ++co)
+#pragma unroll
+      for (int k = 0; k < K; ++k) atomicAdd(dw_s + (co * cin + ci3) * K + k, dwacc[co][k]);
+  }
+  {
+    float v[2 * COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) { v[c] = pacc[c] * sqrtC; v[COUT + c] = pacc[3 * COUT + c]; }
+    const float tot = block_sum2c(v);   // its barriers also publish dw_s
+    if (tid < COUT) { if (a.dg && has_g && has_u) atomicAdd(a.dg + tid, tot); }
+    else if (tid < 2 * COUT) { if (a.db) atomicAdd(a.db + tid - COUT, tot); }
+  }
+  for (int i = tid; i < COUT * cin * K; i += NT) atomicAdd(a.dw + i, dw_s[i]);
+}
+
+template <int COUT, int K, int P, int NT>
+static int launch_fused_tma(ConvBwdFusedArgs a, cudaStream_t st) {
+  constexpr int TL = NT * P, TS = TL + 36, NW = NT / 32;
+  const int cin = a.c1 + a.c2;
+  const int rows = (a.u ? 2 * COUT : COUT) + cin;
+  a.tiles_per_row = (a.L + TL - 1) / TL;
+  a.total_tiles = a.tiles_per_row * a.R;
+  size_t smem = sizeof(float) * ((size_t)2 * rows * TS + (size_t)COUT * TS + (size_t)COUT * cin * 4 + (size_t)COUT * cin * K +
+                                 NW * 2 * COUT + 2) + 16;
+  if (smem > 220 * 1024) return -6;
+  auto kern = conv_bwd_fused_tma_kernel<COUT, K, P, NT>;
+  static int sm_count = 0;
+  if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+  if (occ < 1) return -6;
+  int grid = min(a.total_tiles, sm_count * occ);
+  a.tiles_per_cta = (a.total_tiles + grid - 1) / grid;
+  grid = (a.total_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
+  kern<<<(unsigned)grid, NT, smem, st>>>(a);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int COUT, int K, int P, int VEC>
+static int launch_fused(ConvBwdFusedArgs a, cudaStream_t st) {
+  constexpr int TL = 128 * P, DS = TL + 4;
+  const int cin = a.c1 + a.c2;
+  a.tiles_per_row = (a.L + TL - 1) / TL;
+  a.total_tiles = a.tiles_per_row * a.R;
+  size_t smem = sizeof(float) * ((size_t)COUT * DS + 8 + (size_t)cin * DS + 8 + (size_t)COUT * cin * 4 + (size_t)COUT * cin * K + 4 * 4 * COUT);
+  auto kern = conv_bwd_fused_kernel<COUT, K, P, VEC>;
+  static int sm_count = 0;
+  if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem);
+  if (occ < 1) return -6;
+  int grid = min(a.total_tiles, sm_count * occ);
+  a.tiles_per_cta = (a.total_tiles + grid - 1) / grid;
+  grid = (a.total_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
+  kern<<<(unsigned)grid, 128, smem, st>>>(a);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int K>
+static int dispatch_fused(const ConvBwdFusedArgs& a, int cout, cudaStream_t st) {
+  const bool v4 = (a.L % 4 == 0);
+  // 16-byte aligned rows: bulk-async-copy pipeline
+  const bool al = v4 && ((((size_t)a.dy | (size_t)a.x1 | (size_t)a.u | (size_t)a.x2) & 15) == 0);
+  static int mode = -1;   // DQ_CONV_BWD_NOTMA=1 forces the plain-load kernels (cross-check)
+  if (mode < 0) { const char* e = getenv("DQ_CONV_BWD_NOTMA"); mode = (e && e[0] == '1') ? 1 : 0; }
+  if (al && mode == 0 && a.L >= 256) {
+    switch (cout) {
+      case 4: return launch_fused_tma<4, K, 4, 128>(a, st);
+      case 8: return launch_fused_tma<8, K, 2, 128>(a, st);
+      case 12: return launch_fused_tma<12, K, 2, 128>(a, st);
+      default: break;
+    }
+  }
+  switch (cout) {
+    case 1: return launch_fused<1, K, 4, 1>(a, st);
+    case 4: return v4 ? launch_fused<4, K, 4, 4>(a, st) : launch_fused<4, K, 4, 1>(a, st);
+    case 8: return v4 ? launch_fused<8, K, 4, 4>(a, st) : launch_fused<8, K, 4, 1>(a, st);
+    case 12: return launch_fused<12, K, 2, 1>(a, st);
+    case 16: return launch_fused<16, K, 2, 1>(a, st);
+    case 24: return launch_fused<24, K, 1, 1>(a, st);
+    case 32: return launch_fused<32, K, 1, 1>(a, st);
+    default: return -3;
+  }
+}
+
+}  // namespace dq
+
+using namespace dq;
+
+// Fused backward of a stride-1 Conv1d(K in {1,3}, pad (K-1)/2) and (if u != NULL) its RMSNorm / scale-shift /
+// activation epilogue.  dx1/dx2 NULL = not needed; acc = accumulate into the destination; dadd (shape of dx1) is added
+// to dx1.  dw / db / dg / dss are accumulated.
+DQ_API int dq_conv_bwd_fused(const float* dy, const float* u, const float* g, const float* ss, int ss_stride, int act,
+                             const float* x1, int c1, const float* x2, int c2, const float* w, const float* dadd,
+                             float* dx1, int acc1, float* dx2, int acc2, float* dw, float* db, float* dg, float* dss,
+                             int cout, int K, int R, int L, int rows_per_sample, void* stream) {
+  ConvBwdFusedArgs a{dy, u, g, ss, x1, x2, w, dadd, dx1, dx2, dw, db, dg, dss, c1, c2, R, L, rows_per_sample, ss_stride,
+                     act, acc1, acc2, 0, 0, 0};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (R <= 0 || L <= 0) return 0;
+  if (c1 + c2 > 64) return -3;
+  if (K == 3) return dispatch_fused<3>(a, cout, st);
+  if (K == 1) return dispatch_fused<1>(a, cout, st);
+  return -2;
+}

@@ -25,6 +25,7 @@ _SIGS = {
     "dq_block_bwd": ("ppppiipppiiiis", 1),
     "dq_conv1d_bwd_data": ("pppiipiiiiiiiiiis", 1),
     "dq_conv1d_bwd_weight": ("ppipipippiiiiiiiiis", 1),
+    "dq_conv_bwd_fused": ("ppppiipipipppipippppiiiiis", 1),
     "dq_sample_dot": ("ppppilis", 1),
     "dq_linattn_fwd": ("pppppppppppiiis", 3),
     "dq_linattn_bwd": ("pppppppppppppppppppiiis", 3),

@@ -400,6 +400,9 @@ class UNet1d(nn.Module):
     def _conv_bwd(self, du, x1, x2, wname, bname, K, stride, pad, up, need_dx1=True, need_dx2=True, dx1=None,
                   dx2=None, in_ss=None, rps=1):
         """Accumulates dW/db; returns (dx1, dx2).  If dx1/dx2 tensors are passed the result is ACCUMULATED into them."""
+        if K in (1, 3) and stride == 1 and up == 1 and in_ss is None:
+            return self._conv_bwd_fused(du, None, None, None, ACT_NONE, x1, x2, wname, bname, K, need_dx1, need_dx2,
+                                        dx1, dx2, None, rps)
         R, cout, Lout = du.shape
         c1, Lin = x1.shape[1], x1.shape[2]
         c2 = x2.shape[1] if x2 is not None else 0
@@ -415,6 +418,27 @@ class UNet1d(nn.Module):
         if (need_dx1 or (need_dx2 and c2)):
             N.call("dq_conv1d_bwd_data", du, self._w(wname), dx1 if need_dx1 else None, c1, acc1,
                    dx2 if (need_dx2 and c2) else None, c2, acc2, cout, K, stride, pad, up, R, Lin, Lout)
+        return dx1, dx2
+
+    def _conv_bwd_fused(self, dy, u, g, ss, act, x1, x2, wname, bname, K, need_dx1=True, need_dx2=True, dx1=None,
+                        dx2=None, dadd=None, rps=1):
+        """One-pass backward of a stride-1 conv (K in {1, 3}) and, if `u` is given, of its RMSNorm / scale-shift /
+        activation epilogue: dx1/dx2 (accumulated into the passed tensors, `dadd` added to dx1), dW, db, dg, dSS."""
+        R, cout, L = dy.shape
+        c1 = x1.shape[1]
+        c2 = x2.shape[1] if x2 is not None else 0
+        acc1 = 1 if dx1 is not None else 0
+        acc2 = 1 if dx2 is not None else 0
+        if need_dx1 and dx1 is None:
+            dx1 = self._empty(R, c1, L)
+        if need_dx2 and c2 and dx2 is None:
+            dx2 = self._empty(R, c2, L)
+        ssp, sss = (None, 0) if ss is None else (self._SS[:, ss:], self.ss_total)
+        dssp = None if ss is None else self._dSS[:, ss:]
+        N.call("dq_conv_bwd_fused", dy, u, self._w(g) if g else None, _off_ptr(ssp), sss, act, x1, c1, x2, c2,
+               self._w(wname), dadd, dx1 if need_dx1 else None, acc1, dx2 if (need_dx2 and c2) else None, acc2,
+               self._gw(wname), self._gw(bname) if bname else None, self._gw(g) if g else None, _off_ptr(dssp),
+               cout, K, R, L, rps)
         return dx1, dx2
 
     def _block_bwd(self, dy, u, g, ss, act, rps):
@@ -442,16 +466,16 @@ class UNet1d(nn.Module):
 
     def _resnet_bwd(self, pre, saved, dout, rps, need_dx=True):
         x1, x2, u1, h1, u2 = saved
-        du2 = self._block_bwd(dout, u2, pre + ".block2.norm.g", None, ACT_SILU, rps)
-        dh1, _ = self._conv_bwd(du2, h1, None, pre + ".block2.proj.weight", pre + ".block2.proj.bias", 3, 1, 1, 1, rps=rps)
-        du1 = self._block_bwd(dh1, u1, pre + ".block1.norm.g", self.ss_off[pre + ".mlp.1"], ACT_SILU, rps)
-        dx1, dx2 = self._conv_bwd(du1, x1, x2, pre + ".block1.proj.weight", pre + ".block1.proj.bias", 3, 1, 1, 1,
-                                  need_dx1=need_dx, need_dx2=need_dx, rps=rps)
-        if (pre + ".res_conv.weight") in self.specs:
-            dx1, dx2 = self._conv_bwd(dout, x1, x2, pre + ".res_conv.weight", pre + ".res_conv.bias", 1, 1, 0, 1,
-                                      need_dx1=need_dx, need_dx2=need_dx, dx1=dx1, dx2=dx2, rps=rps)
-        elif need_dx:
-            N.call("dq_add_inplace", dx1, dout, dx1.numel())
+        dh1, _ = self._conv_bwd_fused(dout, u2, pre + ".block2.norm.g", None, ACT_SILU, h1, None,
+                                      pre + ".block2.proj.weight", pre + ".block2.proj.bias", 3, rps=rps)
+        has_res = (pre + ".res_conv.weight") in self.specs
+        dx1, dx2 = self._conv_bwd_fused(dh1, u1, pre + ".block1.norm.g", self.ss_off[pre + ".mlp.1"], ACT_SILU, x1, x2,
+                                        pre + ".block1.proj.weight", pre + ".block1.proj.bias", 3, need_dx1=need_dx,
+                                        need_dx2=need_dx, dadd=None if (has_res or not need_dx) else dout, rps=rps)
+        if has_res:
+            dx1, dx2 = self._conv_bwd_fused(dout, None, None, None, ACT_NONE, x1, x2, pre + ".res_conv.weight",
+                                            pre + ".res_conv.bias", 1, need_dx1=need_dx, need_dx2=need_dx, dx1=dx1,
+                                            dx2=dx2, rps=rps)
         return dx1, dx2
 
     def _la_fwd(self, pre, x, save):

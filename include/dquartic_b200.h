@@ -53,6 +53,12 @@ int dq_conv1d_bwd_data(const float* du, const float* w, float* dx1, int c1, int 
 int dq_conv1d_bwd_weight(const float* du, const float* x1, int c1, const float* x2, int c2, const float* in_ss,
                          int in_ss_stride, float* dw, float* db, int cout, int K, int stride, int pad, int up,
                          int R, int Lin, int Lout, int rows_per_sample, void* stream);
+/* Fused backward of a stride-1 Conv1d (K = 1 or 3, pad (K-1)/2) and, if u != NULL, of its Block epilogue
+ * (unet1d.py:248-268, 302-323): one pass computes du, dx1/dx2 (+dadd, optional accumulate), dW, db, dg, d scale/shift. */
+int dq_conv_bwd_fused(const float* dy, const float* u, const float* g, const float* ss, int ss_stride, int act,
+                      const float* x1, int c1, const float* x2, int c2, const float* w, const float* dadd,
+                      float* dx1, int acc1, float* dx2, int acc2, float* dw, float* db, float* dg, float* dss,
+                      int cout, int K, int R, int L, int rows_per_sample, void* stream);
 /* gradient of ConditionalScaleShift (unet1d.py:677-678): per-sample sum d*c and sum d. */
 int dq_sample_dot(const float* d, const float* c, float* dscale, float* dshift, int out_stride, long n_per_sample,
                   int n_samples, void* stream);

@@ -32,6 +32,7 @@ for pre, c1, c2, L in [("downs.0.0", 4, 0, 40000), ("ups.6.0", 4, 4, 40000), ("d
     dx1 = torch.empty_like(x1); dx2 = torch.empty_like(x2) if c2 else None
     t_d = tm(lambda: N.call("dq_conv1d_bwd_data", du, net._w(w), dx1, c1, 0, dx2, c2, 0, cout, 3, 1, 1, 1, R, L, L))
     t_w = tm(lambda: N.call("dq_conv1d_bwd_weight", du, x1, c1, x2, c2, None, 0, net._gw(w), net._gw(bn), cout, 3, 1, 1, 1, R, L, L, rt))
+    t_fu = tm(lambda: net._conv_bwd_fused(dy, u, gname, net.ss_off[pre + ".mlp.1"], 1, x1, x2, w, bn, 3, rps=rt))
     cin = c1 + c2
     hb = lambda mb: mb / 6.55e3 * 1000  # us at 6.55 TB/s
-    print(f"{pre} cin={cin} cout={cout} L={L}: fwd {t_f:.0f} us (hbm {hb(elt*(cin+2*cout)):.0f}) | block_bwd {t_b:.0f} (hbm {hb(elt*3*cout):.0f}) | bwd_data {t_d:.0f} (hbm {hb(elt*(cin+cout)):.0f}) | bwd_weight {t_w:.0f} (hbm {hb(elt*(cin+cout)):.0f})")
+    print(f"{pre} cin={cin} cout={cout} L={L}: fwd {t_f:.0f} us (hbm {hb(elt*(cin+2*cout)):.0f}) | block_bwd {t_b:.0f} (hbm {hb(elt*3*cout):.0f}) | bwd_data {t_d:.0f} (hbm {hb(elt*(cin+cout)):.0f}) | bwd_weight {t_w:.0f} (hbm {hb(elt*(cin+cout)):.0f}) || FUSED bwd {t_fu:.0f} (hbm {hb(elt*(2*cout+2*cin)):.0f})")
