@@ -420,6 +420,12 @@ static int launch_bwd_weight(ConvBwdWeightArgs a, cudaStream_t st) {
 
 using namespace dq;
 
+namespace dq {
+int conv_fwd_tma_try(const float* x1, int c1, const float* x2, int c2, const float* w, const float* bias, int cout, int K,
+                     const float* g, const float* ss, int ss_stride, int act, const float* res, float* u, float* y, int R,
+                     int L, int rows_per_sample, cudaStream_t st);
+}
+
 // C-ABI ---------------------------------------------------------------------------------------------------------
 DQ_API int dq_conv1d_fwd(const float* x1, int c1, const float* x2, int c2, const float* in_ss, int in_ss_stride,
                          const float* w, const float* bias, int cout, int K, int stride, int pad, int up,
@@ -429,6 +435,10 @@ DQ_API int dq_conv1d_fwd(const float* x1, int c1, const float* x2, int c2, const
                 in_ss_stride, act};
   cudaStream_t st = (cudaStream_t)stream;
   if (R <= 0 || Lout <= 0) return 0;
+  if (stride == 1 && up == 1 && !in_ss && Lin == Lout && pad == (K - 1) / 2) {   // bulk-copy pipelined kernel (conv_fused.cu)
+    int rc = conv_fwd_tma_try(x1, c1, x2, c2, w, bias, cout, K, g, ss, ss_stride, act, res, u, y, R, Lout, rows_per_sample, st);
+    if (rc != 0) return rc < 0 ? rc : 0;
+  }
   switch (cout) {
     case 1: return dispatch_fwd_mode<1>(a, K, stride, up, st);
     case 4: return dispatch_fwd_mode<4>(a, K, stride, up, st);

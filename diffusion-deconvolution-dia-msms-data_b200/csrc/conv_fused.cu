@@ -804,6 +804,217 @@ static int dispatch_fused(const ConvBwdFusedArgs& a, int cout, cudaStream_t st) 
   }
 }
 
+// =====================================================================================================================
+// Pipelined forward of a stride-1 Conv1d (K = 1 or 3) with the fused Block epilogue (bias, RMSNorm over channels,
+// per-sample scale/shift, SiLU/GELU, residual add): Block.forward unet1d.py:248-268, ResnetBlock 302-323.
+// The input rows (both concat sources, and the residual rows) of a tile arrive by bulk async copies, two tiles deep;
+// a thread owns P consecutive positions and all COUT output channels (needed for the channel RMSNorm), reads its
+// taps with one 128/64-bit shared load + 2 neighbours per input channel and the weights as broadcast float4.
+struct ConvFwdTmaArgs {
+  const float* x1; const float* x2; const float* w; const float* bias; const float* g; const float* ss;
+  const float* res; float* u; float* y;
+  int c1, c2, R, L, rows_per_sample, ss_stride, act, tiles_per_row, total_tiles, tiles_per_cta;
+};
+
+template <int COUT, int K, int P, int NT>
+__global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
+  constexpr int TL = NT * P;
+  constexpr int TS = TL + 36;
+  constexpr int H = (K - 1) / 2;
+  static_assert(P == 2 || P == 4, "P");
+  static_assert(COUT % 4 == 0, "COUT");
+  extern __shared__ float4 dyn_smem4[];
+  const int cin = a.c1 + a.c2;
+  const bool has_res = a.res != nullptr;
+  const int rows = cin + (has_res ? COUT : 0);
+  float* stage0 = reinterpret_cast<float*>(dyn_smem4);
+  const int stage_floats = rows * TS;
+  float* w_s = stage0 + 2 * stage_floats;                 // [(ci*K + k) * COUT + co]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + cin * K * COUT);
+  const int tid = threadIdx.x;
+  const uint32_t bar0 = cf_smem_u32(bars), bar1 = bar0 + 8;
+  if (tid == 0) {
+    cf_mbar_init(bar0, 1);
+    cf_mbar_init(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < cin * K * COUT; i += NT) {
+    const int co = i % COUT, ck = i / COUT;
+    w_s[i] = a.w[(size_t)co * cin * K + ck];
+  }
+  __syncthreads();
+  const int t_begin = blockIdx.x * a.tiles_per_cta, t_end = min(a.total_tiles, t_begin + a.tiles_per_cta);
+  const int n_tiles = t_end - t_begin;
+
+  auto issue = [&](int tile, int s) {
+    if (tid < 32) {
+      const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
+      const int l_lo = max(0, tl0 - 4), l_hi = min(a.L, tl0 + TL + 4);
+      const uint32_t bytes = (uint32_t)(l_hi - l_lo) * 4u;
+      const uint32_t bar = s ? bar1 : bar0;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (tid == 0) cf_mbar_expect_tx(bar, bytes * (uint32_t)rows);
+      __syncwarp();
+      float* st = stage0 + s * stage_floats;
+      for (int row = tid; row < rows; row += 32) {
+        const float* src;
+        if (row < a.c1) src = a.x1 + ((size_t)r * a.c1 + row) * a.L;
+        else if (row < cin) src = a.x2 + ((size_t)r * a.c2 + (row - a.c1)) * a.L;
+        else src = a.res + ((size_t)r * COUT + (row - cin)) * a.L;
+        cf_bulk_g2s(cf_smem_u32(st + row * TS + (l_lo - (tl0 - 4))), src + l_lo, bytes, bar);
+      }
+    }
+  };
+  if (n_tiles > 0) issue(t_begin, 0);
+  if (n_tiles > 1) issue(t_begin + 1, 1);
+
+  const float sqrtC = sqrtf((float)COUT);
+  const bool has_g = a.g != nullptr, has_ss = a.ss != nullptr;
+  float bias[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) bias[c] = a.bias ? a.bias[c] : 0.f;
+
+  for (int it = 0; it < n_tiles; ++it) {
+    const int tile = t_begin + it, s = it & 1;
+    const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
+    const int sample = r / a.rows_per_sample;
+    float* x_t = stage0 + s * stage_floats;
+    cf_mbar_wait(s ? bar1 : bar0, (uint32_t)((it >> 1) & 1));
+    if (H > 0) {   // zero padding at the two row ends (positions -1 and L)
+      if (tid < cin) {
+        if (tl0 == 0) x_t[tid * TS + 3] = 0.f;
+        if (a.L <= tl0 + TL) x_t[tid * TS + (a.L - tl0 + 4)] = 0.f;
+      }
+      if (tl0 == 0 || a.L <= tl0 + TL) __syncthreads();   // uniform per tile
+    }
+    const int l = tl0 + P * tid;
+    const bool ok = l < a.L;
+    float acc[P][COUT];
+#pragma unroll
+    for (int i = 0; i < P; ++i)
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) acc[i][c] = bias[c];
+#pragma unroll 2
+    for (int ci = 0; ci < cin; ++ci) {
+      float xw[P + 2];
+      const float* xr = x_t + ci * TS + 4 + P * tid;
+      if (P == 4) { const float4 m = *reinterpret_cast<const float4*>(xr); xw[1] = m.x; xw[2] = m.y; xw[3] = m.z; xw[4] = m.w; }
+      else { const float2 m = *reinterpret_cast<const float2*>(xr); xw[1] = m.x; xw[2] = m.y; }
+      if (K == 3) { xw[0] = xr[-1]; xw[P + 1] = xr[P]; }
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float4* wp = reinterpret_cast<const float4*>(w_s + (ci * K + k) * COUT);
+#pragma unroll
+        for (int c4 = 0; c4 < COUT / 4; ++c4) {
+          const float4 w4 = wp[c4];
+#pragma unroll
+          for (int i = 0; i < P; ++i) {
+            const float xv = xw[i + 1 + k - H];
+            acc[i][4 * c4 + 0] = fmaf(xv, w4.x, acc[i][4 * c4 + 0]);
+            acc[i][4 * c4 + 1] = fmaf(xv, w4.y, acc[i][4 * c4 + 1]);
+            acc[i][4 * c4 + 2] = fmaf(xv, w4.z, acc[i][4 * c4 + 2]);
+            acc[i][4 * c4 + 3] = fmaf(xv, w4.w, acc[i][4 * c4 + 3]);
+          }
+        }
+      }
+    }
+    if (ok) {
+      const size_t base = (size_t)r * COUT * a.L + l;
+      if (a.u) {
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          if (P == 4) *reinterpret_cast<float4*>(a.u + base + (size_t)c * a.L) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+          else *reinterpret_cast<float2*>(a.u + base + (size_t)c * a.L) = make_float2(acc[0][c], acc[1][c]);
+        }
+      }
+      float gs[COUT], sh[COUT];
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        const float sc1 = has_ss ? a.ss[(size_t)sample * a.ss_stride + c] + 1.f : 1.f;
+        gs[c] = (has_g ? a.g[c] * sqrtC : 1.f) * sc1;
+        sh[c] = has_ss ? a.ss[(size_t)sample * a.ss_stride + COUT + c] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        float inv = 1.f;
+        if (has_g) {
+          float s2 = 0.f;
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) s2 = fmaf(acc[i][c], acc[i][c], s2);
+          inv = s2 > 1e-24f ? cf_rsqrt(s2) : 1e12f;
+        }
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          float z = fmaf(acc[i][c] * inv, gs[c], sh[c]);
+          if (a.act == 1) z = z * cf_rcp(1.f + cf_ex2(-1.4426950408889634f * z));
+          else if (a.act == 2) z = act_fwd(z, 2);
+          if (has_res) z += x_t[(cin + c) * TS + 4 + P * tid + i];
+          acc[i][c] = z;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        if (P == 4) *reinterpret_cast<float4*>(a.y + base + (size_t)c * a.L) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+        else *reinterpret_cast<float2*>(a.y + base + (size_t)c * a.L) = make_float2(acc[0][c], acc[1][c]);
+      }
+    }
+    __syncthreads();   // everyone is done with stage s
+    if (it + 2 < n_tiles) issue(tile + 2, s);
+  }
+}
+
+template <int COUT, int K, int P, int NT>
+static int launch_fwd_tma(ConvFwdTmaArgs a, cudaStream_t st) {
+  constexpr int TL = NT * P, TS = TL + 36;
+  const int cin = a.c1 + a.c2;
+  const int rows = cin + (a.res ? COUT : 0);
+  a.tiles_per_row = (a.L + TL - 1) / TL;
+  a.total_tiles = a.tiles_per_row * a.R;
+  size_t smem = sizeof(float) * ((size_t)2 * rows * TS + (size_t)cin * K * COUT) + 16;
+  if (smem > 220 * 1024) return -6;
+  auto kern = conv_fwd_tma_kernel<COUT, K, P, NT>;
+  static int sm_count = 0;
+  if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+  if (occ < 1) return -6;
+  int grid = min(a.total_tiles, sm_count * occ);
+  a.tiles_per_cta = (a.total_tiles + grid - 1) / grid;
+  grid = (a.total_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
+  kern<<<(unsigned)grid, NT, smem, st>>>(a);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// Returns 1 if the pipelined kernel took the call, 0 if the shape / alignment is not eligible, < 0 on error.
+int conv_fwd_tma_try(const float* x1, int c1, const float* x2, int c2, const float* w, const float* bias, int cout, int K,
+                     const float* g, const float* ss, int ss_stride, int act, const float* res, float* u, float* y, int R,
+                     int L, int rows_per_sample, cudaStream_t st) {
+  static int mode = -1;   // DQ_CONV_FWD_NOTMA=1 forces the plain-load kernel (cross-check)
+  if (mode < 0) { const char* e = getenv("DQ_CONV_FWD_NOTMA"); mode = (e && e[0] == '1') ? 1 : 0; }
+  if (mode == 1 || (K != 1 && K != 3) || L % 4 != 0 || L < 256 || c1 + c2 > 64) return 0;
+  if ((((size_t)x1 | (size_t)x2 | (size_t)res | (size_t)u | (size_t)y) & 15) != 0) return 0;
+  ConvFwdTmaArgs a{x1, x2, w, bias, g, ss, res, u, y, c1, c2, R, L, rows_per_sample, ss_stride, act, 0, 0, 0};
+  int rc;
+  if (K == 3) {
+    switch (cout) {
+      case 4: rc = launch_fwd_tma<4, 3, 4, 128>(a, st); break;
+      case 8: rc = launch_fwd_tma<8, 3, 4, 128>(a, st); break;
+      case 12: rc = launch_fwd_tma<12, 3, 2, 128>(a, st); break;
+      default: return 0;
+    }
+  } else {
+    switch (cout) {
+      case 4: rc = launch_fwd_tma<4, 1, 4, 128>(a, st); break;
+      case 8: rc = launch_fwd_tma<8, 1, 4, 128>(a, st); break;
+      case 12: rc = launch_fwd_tma<12, 1, 2, 128>(a, st); break;
+      default: return 0;
+    }
+  }
+  return rc == 0 ? 1 : rc;
+}
+
 }  // namespace dq
 
 using namespace dq;
