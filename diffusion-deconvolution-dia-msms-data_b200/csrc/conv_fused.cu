@@ -401,25 +401,24 @@ __device__ __forceinline__ float cf_dsilu(float z) {
   return s * fmaf(z, 1.f - s, 1.f);
 }
 
-template <int COUT, int K, int P, int NT>
+// EPI = false: plain conv (du = dy).  EPI = true: RMSNorm (g) + optional per-sample scale/shift + SiLU epilogue.
+template <int COUT, int K, int P, int NT, bool EPI>
 __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs a) {
   constexpr int TL = NT * P;
   constexpr int TS = TL + 36;
   constexpr int H = (K - 1) / 2;
-  constexpr int NPA = 4 * COUT;
   constexpr int NW = NT / 32;
+  constexpr int DYR = EPI ? 2 * COUT : COUT;             // dy rows, [u rows]
   static_assert(P == 2 || P == 4, "P");
   extern __shared__ float4 dyn_smem4[];
-  const int cin = a.c1 + a.c2;
-  const bool has_u = a.u != nullptr;
-  const int rows = (has_u ? 2 * COUT : COUT) + cin;      // dy rows, [u rows], x rows
+  const int cin = a.c1 + a.c2;                           // multiple of 4 (checked by the launcher), as is c1
+  const int rows = DYR + cin;
   float* stage0 = reinterpret_cast<float*>(dyn_smem4);
   const int stage_floats = rows * TS;
-  float* du_s = stage0 + 2 * stage_floats;               // COUT * TS
-  float* w_s = du_s + COUT * TS;                         // COUT * cin * 4
+  float* w_s = stage0 + 2 * stage_floats;                // COUT * cin * 4
   float* dw_s = w_s + COUT * cin * 4;                    // COUT * cin * K
   float* red = dw_s + COUT * cin * K;                    // NW * 2 * COUT
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red + NW * 2 * COUT + ((NW * 2 * COUT) & 1));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + NW * 2 * COUT);
   const int tid = threadIdx.x;
   const uint32_t bar0 = cf_smem_u32(bars), bar1 = bar0 + 8;
 
@@ -452,9 +451,9 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
       for (int row = tid; row < rows; row += 32) {
         const float* src;
         if (row < COUT) src = a.dy + ((size_t)r * COUT + row) * a.L;
-        else if (has_u && row < 2 * COUT) src = a.u + ((size_t)r * COUT + (row - COUT)) * a.L;
+        else if (row < DYR) src = a.u + ((size_t)r * COUT + (row - COUT)) * a.L;
         else {
-          const int ci = row - (has_u ? 2 * COUT : COUT);
+          const int ci = row - DYR;
           src = (ci < a.c1) ? a.x1 + ((size_t)r * a.c1 + ci) * a.L : a.x2 + ((size_t)r * a.c2 + (ci - a.c1)) * a.L;
         }
         cf_bulk_g2s(cf_smem_u32(st + row * TS + (l_lo - (tl0 - 4))), src + l_lo, bytes, bar);
@@ -475,11 +474,12 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
   for (int co = 0; co < COUT; ++co)
 #pragma unroll
     for (int k = 0; k < K; ++k) dwacc[co][k] = 0.f;
-  float pacc[NPA];
+  // per-thread partial sums: S = sum d*uhat, T = sum d (current sample), B = sum du (bias), G = d g / sqrt(C)
+  float accS[COUT], accT[COUT], accB[COUT], accG[COUT];
 #pragma unroll
-  for (int i = 0; i < NPA; ++i) pacc[i] = 0.f;
+  for (int c = 0; c < COUT; ++c) accS[c] = accT[c] = accB[c] = accG[c] = 0.f;
   const float sqrtC = sqrtf((float)COUT);
-  const bool has_g = a.g != nullptr, has_ss = a.ss != nullptr, silu = a.act == 1;
+  const bool has_ss = a.ss != nullptr;
   int cur_sample = -1;
 
   auto block_sum2c = [&](float (&v)[2 * COUT]) -> float {   // thread i < 2*COUT returns the block total of v[i]
@@ -496,76 +496,68 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
     __syncthreads();
     return out;
   };
+  // d scale[c] = g[c] sqrt(C) S[c], d shift[c] = T[c] leave the CTA when the sample changes; d g picks up scale1 * S
   auto flush_sample = [&](int sample) {
     float v[2 * COUT];
 #pragma unroll
-    for (int c = 0; c < 2 * COUT; ++c) { v[c] = pacc[COUT + c]; pacc[COUT + c] = 0.f; }
-    const float tot = block_sum2c(v);
-    if (a.dss && has_ss && tid < 2 * COUT) atomicAdd(a.dss + (size_t)sample * a.ss_stride + tid, tot);
+    for (int c = 0; c < COUT; ++c) {
+      const float sc1 = has_ss ? a.ss[(size_t)sample * a.ss_stride + c] + 1.f : 1.f;
+      accG[c] = fmaf(sc1, accS[c], accG[c]);
+      v[c] = accS[c] * a.g[c] * sqrtC;
+      v[COUT + c] = accT[c];
+      accS[c] = 0.f; accT[c] = 0.f;
+    }
+    if (a.dss && has_ss) {   // CTA-uniform
+      const float tot = block_sum2c(v);
+      if (tid < 2 * COUT) atomicAdd(a.dss + (size_t)sample * a.ss_stride + tid, tot);
+    }
   };
 
   for (int it = 0; it < n_tiles; ++it) {
     const int tile = t_begin + it, s = it & 1;
     const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
     const int sample = r / a.rows_per_sample;
-    if (sample != cur_sample) {
-      if (cur_sample >= 0 && has_u) flush_sample(cur_sample);
+    if (EPI && sample != cur_sample) {
+      if (cur_sample >= 0) flush_sample(cur_sample);
       cur_sample = sample;
     }
-    const float* dy_t = stage0 + s * stage_floats;           // [COUT][TS]
-    const float* u_t = dy_t + COUT * TS;                     // [COUT][TS] (if has_u)
-    float* x_t = stage0 + s * stage_floats + (has_u ? 2 * COUT : COUT) * TS;   // [cin][TS]
+    float* du_s = stage0 + s * stage_floats;                 // dy rows, overwritten in place by du
+    const float* u_t = du_s + COUT * TS;                     // [COUT][TS] (EPI only)
+    float* x_t = du_s + DYR * TS;                            // [cin][TS]
     cf_mbar_wait(s ? bar1 : bar0, (uint32_t)((it >> 1) & 1));
 
-    // ---------------------------------------------------------------- phase 1: du tile
-    {
-      float gl[COUT], scale1[COUT], shift[COUT];
+    // ---------------------------------------------------------------- phase 1: du tile (in place of dy)
+    if (EPI) {
+      float gs[COUT], shift[COUT];
 #pragma unroll
       for (int c = 0; c < COUT; ++c) {
-        gl[c] = has_g ? a.g[c] * sqrtC : 1.f;
-        scale1[c] = has_ss ? a.ss[(size_t)sample * a.ss_stride + c] + 1.f : 1.f;
+        const float sc1 = has_ss ? a.ss[(size_t)sample * a.ss_stride + c] + 1.f : 1.f;
+        gs[c] = a.g[c] * sqrtC * sc1;
         shift[c] = has_ss ? a.ss[(size_t)sample * a.ss_stride + COUT + c] : 0.f;
       }
       // inputs of non-existent positions are zeroed at load time, which makes every derived quantity exactly 0
-      auto du_at = [&](const float (&dyv)[COUT], const float (&uvin)[COUT], float (&duv)[COUT], bool accumulate) {
-        if (!has_u) {
-#pragma unroll
-          for (int c = 0; c < COUT; ++c) {
-            duv[c] = dyv[c];
-            if (accumulate) pacc[3 * COUT + c] += duv[c];
-          }
-          return;
-        }
+      auto du_at = [&](float (&dv)[COUT], const float (&uvin)[COUT], bool accumulate) {   // dv: dy in, du out
         float uh[COUT];
         float s2 = 0.f;
 #pragma unroll
         for (int c = 0; c < COUT; ++c) s2 = fmaf(uvin[c], uvin[c], s2);
         const bool big = s2 > 1e-24f;                        // ||u|| > 1e-12 (F.normalize eps)
-        const float inv = has_g ? (big ? cf_rsqrt(s2) : 1e12f) : 1.f;
+        const float inv = big ? cf_rsqrt(s2) : 1e12f;
         float dot = 0.f;
 #pragma unroll
         for (int c = 0; c < COUT; ++c) {
           uh[c] = uvin[c] * inv;
-          const float n = uh[c] * gl[c];                     // gl already carries sqrt(C) (or 1 without norm)
-          const float z = fmaf(n, scale1[c], shift[c]);
-          const float d = dyv[c] * (silu ? cf_dsilu(z) : act_bwd(z, a.act));
-          const float dn = d * scale1[c];
-          if (accumulate) {
-            pacc[c] += dn * uh[c];                           // d g / sqrt(C)
-            pacc[COUT + c] += d * n;                         // d scale
-            pacc[2 * COUT + c] += d;                         // d shift
-          }
-          duv[c] = dn * gl[c];                               // d u-hat (no norm: plain d u)
-          dot = fmaf(duv[c], uh[c], dot);
+          const float z = fmaf(uh[c], gs[c], shift[c]);
+          const float d = dv[c] * cf_dsilu(z);
+          if (accumulate) { accS[c] = fmaf(d, uh[c], accS[c]); accT[c] += d; }
+          dv[c] = d * gs[c];                                 // d u-hat
+          dot = fmaf(dv[c], uh[c], dot);
         }
-        if (has_g) {
-          const float k = big ? dot : 0.f;
+        const float k = big ? dot : 0.f;
 #pragma unroll
-          for (int c = 0; c < COUT; ++c) duv[c] = (duv[c] - uh[c] * k) * inv;
-        }
-        if (accumulate) {
-#pragma unroll
-          for (int c = 0; c < COUT; ++c) pacc[3 * COUT + c] += duv[c];   // d bias
+        for (int c = 0; c < COUT; ++c) {
+          dv[c] = (dv[c] - uh[c] * k) * inv;
+          if (accumulate) accB[c] += dv[c];
         }
       };
       {
@@ -575,19 +567,15 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
 #pragma unroll
         for (int c = 0; c < COUT; ++c) {
           if (P == 4) {
-            const float4 d4 = *reinterpret_cast<const float4*>(dy_t + c * TS + idx);
+            const float4 d4 = *reinterpret_cast<const float4*>(du_s + c * TS + idx);
             dyv[0][c] = d4.x; dyv[1][c] = d4.y; dyv[2][c] = d4.z; dyv[3][c] = d4.w;
-            if (has_u) {
-              const float4 u4 = *reinterpret_cast<const float4*>(u_t + c * TS + idx);
-              uv[0][c] = u4.x; uv[1][c] = u4.y; uv[2][c] = u4.z; uv[3][c] = u4.w;
-            }
+            const float4 u4 = *reinterpret_cast<const float4*>(u_t + c * TS + idx);
+            uv[0][c] = u4.x; uv[1][c] = u4.y; uv[2][c] = u4.z; uv[3][c] = u4.w;
           } else {
-            const float2 d2 = *reinterpret_cast<const float2*>(dy_t + c * TS + idx);
+            const float2 d2 = *reinterpret_cast<const float2*>(du_s + c * TS + idx);
             dyv[0][c] = d2.x; dyv[1][c] = d2.y;
-            if (has_u) {
-              const float2 u2 = *reinterpret_cast<const float2*>(u_t + c * TS + idx);
-              uv[0][c] = u2.x; uv[1][c] = u2.y;
-            }
+            const float2 u2 = *reinterpret_cast<const float2*>(u_t + c * TS + idx);
+            uv[0][c] = u2.x; uv[1][c] = u2.y;
           }
         }
         if (!ok) {
@@ -596,34 +584,53 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
 #pragma unroll
             for (int c = 0; c < COUT; ++c) { dyv[i][c] = 0.f; uv[i][c] = 0.f; }
         }
-        float o[P][COUT];
 #pragma unroll
-        for (int i = 0; i < P; ++i) du_at(dyv[i], uv[i], o[i], true);
+        for (int i = 0; i < P; ++i) du_at(dyv[i], uv[i], true);
 #pragma unroll
         for (int c = 0; c < COUT; ++c) {
-          if (P == 4) *reinterpret_cast<float4*>(du_s + c * TS + idx) = make_float4(o[0][c], o[1][c], o[2][c], o[3][c]);
-          else *reinterpret_cast<float2*>(du_s + c * TS + idx) = make_float2(o[0][c], o[1][c]);
+          if (P == 4) *reinterpret_cast<float4*>(du_s + c * TS + idx) = make_float4(dyv[0][c], dyv[1][c], dyv[2][c], dyv[3][c]);
+          else *reinterpret_cast<float2*>(du_s + c * TS + idx) = make_float2(dyv[0][c], dyv[1][c]);
         }
       }
       if (H > 0 && (tid == 0 || tid == NT - 1)) {   // halo positions tl0 - 1 and tl0 + TL (no accumulation)
         const int idx = tid == 0 ? 3 : TL + 4;
         const int l = tl0 - 4 + idx;
         const bool ok = l >= 0 && l < a.L;
-        float dyv[COUT], uv[COUT], o[COUT];
+        float dyv[COUT], uv[COUT];
 #pragma unroll
         for (int c = 0; c < COUT; ++c) {
-          dyv[c] = ok ? dy_t[c * TS + idx] : 0.f;
-          uv[c] = (ok && has_u) ? u_t[c * TS + idx] : 0.f;
+          dyv[c] = ok ? du_s[c * TS + idx] : 0.f;
+          uv[c] = ok ? u_t[c * TS + idx] : 0.f;
         }
-        du_at(dyv, uv, o, false);
+        du_at(dyv, uv, false);
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) du_s[c * TS + idx] = o[c];
+        for (int c = 0; c < COUT; ++c) du_s[c * TS + idx] = dyv[c];
       }
-      // x rows: exact zeros at the two out-of-range neighbours a valid du can touch (row start / row end)
-      if (tid < cin) {
-        if (tl0 == 0) x_t[tid * TS + 3] = 0.f;
-        if (a.L <= tl0 + TL) x_t[tid * TS + (a.L - tl0 + 4)] = 0.f;
+    } else {
+      // plain conv: du = dy already sits in the stage; zero the non-existent positions and accumulate the bias gradient
+      const int idx = 4 + P * tid;
+      const bool ok = tl0 + P * tid < a.L;
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        if (P == 4) {
+          float4 d4 = *reinterpret_cast<const float4*>(du_s + c * TS + idx);
+          if (!ok) { d4 = make_float4(0.f, 0.f, 0.f, 0.f); *reinterpret_cast<float4*>(du_s + c * TS + idx) = d4; }
+          accB[c] += (d4.x + d4.y) + (d4.z + d4.w);
+        } else {
+          float2 d2 = *reinterpret_cast<const float2*>(du_s + c * TS + idx);
+          if (!ok) { d2 = make_float2(0.f, 0.f); *reinterpret_cast<float2*>(du_s + c * TS + idx) = d2; }
+          accB[c] += d2.x + d2.y;
+        }
       }
+      if (H > 0 && tid < COUT) {
+        if (tl0 == 0) du_s[tid * TS + 3] = 0.f;
+        if (a.L <= tl0 + TL) du_s[tid * TS + (a.L - tl0 + 4)] = 0.f;
+      }
+    }
+    // x rows: exact zeros at the two out-of-range neighbours a valid du can touch (row start / row end)
+    if (H > 0 && tid < cin) {
+      if (tl0 == 0) x_t[tid * TS + 3] = 0.f;
+      if (a.L <= tl0 + TL) x_t[tid * TS + (a.L - tl0 + 4)] = 0.f;
     }
     __syncthreads();
 
@@ -632,6 +639,18 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
       const int l = tl0 + P * tid;
       const bool ok = l < a.L;
       for (int cb = 0; cb < cin; cb += 4) {
+        float* dst;
+        const float* add = nullptr;
+        int accf;
+        if (cb < a.c1) {
+          dst = a.dx1 ? a.dx1 + ((size_t)r * a.c1 + cb) * a.L + l : nullptr;
+          accf = a.acc1;
+          if (a.dadd) add = a.dadd + ((size_t)r * a.c1 + cb) * a.L + l;
+        } else {
+          dst = a.dx2 ? a.dx2 + ((size_t)r * a.c2 + (cb - a.c1)) * a.L + l : nullptr;
+          accf = a.acc2;
+        }
+        if (!dst) continue;   // CTA-uniform
         float acc[4][P];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -646,43 +665,28 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
           if (K == 3) { dwin[0] = dr[-1]; dwin[P + 1] = dr[P]; }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if (cb + j < cin) {
-              const float4 w4 = *reinterpret_cast<const float4*>(w_s + (co * cin + cb + j) * 4);
-              const float wk[4] = {w4.x, w4.y, w4.z, w4.w};
+            const float4 w4 = *reinterpret_cast<const float4*>(w_s + (co * cin + cb + j) * 4);
+            const float wk[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-              for (int i = 0; i < P; ++i)
+            for (int i = 0; i < P; ++i)
 #pragma unroll
-                for (int k = 0; k < K; ++k) acc[j][i] = fmaf(dwin[i + 1 + H - k], wk[k], acc[j][i]);
-            }
+              for (int k = 0; k < K; ++k) acc[j][i] = fmaf(dwin[i + 1 + H - k], wk[k], acc[j][i]);
           }
         }
         if (ok) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int ci = cb + j;
-            if (ci >= cin) continue;
-            float* dst;
-            int accf;
-            const float* add = nullptr;
-            if (ci < a.c1) {
-              dst = a.dx1 ? a.dx1 + ((size_t)r * a.c1 + ci) * a.L : nullptr;
-              accf = a.acc1;
-              if (a.dadd) add = a.dadd + ((size_t)r * a.c1 + ci) * a.L;
-            } else {
-              dst = a.dx2 ? a.dx2 + ((size_t)r * a.c2 + (ci - a.c1)) * a.L : nullptr;
-              accf = a.acc2;
-            }
-            if (!dst) continue;
+            float* d = dst + (size_t)j * a.L;
             if (P == 4) {
               float4 v = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-              if (add) { const float4 q = __ldg(reinterpret_cast<const float4*>(add + l)); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
-              if (accf) { const float4 q = *reinterpret_cast<const float4*>(dst + l); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
-              *reinterpret_cast<float4*>(dst + l) = v;
+              if (add) { const float4 q = __ldg(reinterpret_cast<const float4*>(add + (size_t)j * a.L)); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+              if (accf) { const float4 q = *reinterpret_cast<const float4*>(d); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+              *reinterpret_cast<float4*>(d) = v;
             } else {
               float2 v = make_float2(acc[j][0], acc[j][1]);
-              if (add) { const float2 q = __ldg(reinterpret_cast<const float2*>(add + l)); v.x += q.x; v.y += q.y; }
-              if (accf) { const float2 q = *reinterpret_cast<const float2*>(dst + l); v.x += q.x; v.y += q.y; }
-              *reinterpret_cast<float2*>(dst + l) = v;
+              if (add) { const float2 q = __ldg(reinterpret_cast<const float2*>(add + (size_t)j * a.L)); v.x += q.x; v.y += q.y; }
+              if (accf) { const float2 q = *reinterpret_cast<const float2*>(d); v.x += q.x; v.y += q.y; }
+              *reinterpret_cast<float2*>(d) = v;
             }
           }
         }
@@ -707,12 +711,12 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
         }
       }
     }
-    __syncthreads();   // everyone is done with stage s and du_s
+    __syncthreads();   // everyone is done with stage s
     if (it + 2 < n_tiles) issue(tile + 2, s);
   }
 
   // ------------------------------------------------------------------ leave: parameter gradients
-  if (cur_sample >= 0 && has_u) flush_sample(cur_sample);
+  if (EPI && cur_sample >= 0) flush_sample(cur_sample);
   if (p3_active) {
 #pragma unroll
     for (int co = 0; co < COUT; ++co)
@@ -722,25 +726,24 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
   {
     float v[2 * COUT];
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) { v[c] = pacc[c] * sqrtC; v[COUT + c] = pacc[3 * COUT + c]; }
+    for (int c = 0; c < COUT; ++c) { v[c] = accG[c] * sqrtC; v[COUT + c] = accB[c]; }
     const float tot = block_sum2c(v);   // its barriers also publish dw_s
-    if (tid < COUT) { if (a.dg && has_g && has_u) atomicAdd(a.dg + tid, tot); }
+    if (tid < COUT) { if (EPI && a.dg) atomicAdd(a.dg + tid, tot); }
     else if (tid < 2 * COUT) { if (a.db) atomicAdd(a.db + tid - COUT, tot); }
   }
   for (int i = tid; i < COUT * cin * K; i += NT) atomicAdd(a.dw + i, dw_s[i]);
 }
 
-template <int COUT, int K, int P, int NT>
+template <int COUT, int K, int P, int NT, bool EPI>
 static int launch_fused_tma(ConvBwdFusedArgs a, cudaStream_t st) {
   constexpr int TL = NT * P, TS = TL + 36, NW = NT / 32;
   const int cin = a.c1 + a.c2;
-  const int rows = (a.u ? 2 * COUT : COUT) + cin;
+  const int rows = (EPI ? 2 * COUT : COUT) + cin;
   a.tiles_per_row = (a.L + TL - 1) / TL;
   a.total_tiles = a.tiles_per_row * a.R;
-  size_t smem = sizeof(float) * ((size_t)2 * rows * TS + (size_t)COUT * TS + (size_t)COUT * cin * 4 + (size_t)COUT * cin * K +
-                                 NW * 2 * COUT + 2) + 16;
+  size_t smem = sizeof(float) * ((size_t)2 * rows * TS + (size_t)COUT * cin * 4 + (size_t)COUT * cin * K + NW * 2 * COUT) + 16;
   if (smem > 220 * 1024) return -6;
-  auto kern = conv_bwd_fused_tma_kernel<COUT, K, P, NT>;
+  auto kern = conv_bwd_fused_tma_kernel<COUT, K, P, NT, EPI>;
   static int sm_count = 0;
   if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -753,6 +756,10 @@ static int launch_fused_tma(ConvBwdFusedArgs a, cudaStream_t st) {
   kern<<<(unsigned)grid, NT, smem, st>>>(a);
   DQ_LAUNCH_CHECK();
   return 0;
+}
+template <int COUT, int K, int P, int NT>
+static int launch_fused_tma_epi(const ConvBwdFusedArgs& a, cudaStream_t st) {
+  return a.u ? launch_fused_tma<COUT, K, P, NT, true>(a, st) : launch_fused_tma<COUT, K, P, NT, false>(a, st);
 }
 
 template <int COUT, int K, int P, int VEC>
@@ -784,11 +791,13 @@ static int dispatch_fused(const ConvBwdFusedArgs& a, int cout, cudaStream_t st) 
   const bool al = v4 && ((((size_t)a.dy | (size_t)a.x1 | (size_t)a.u | (size_t)a.x2) & 15) == 0);
   static int mode = -1;   // DQ_CONV_BWD_NOTMA=1 forces the plain-load kernels (cross-check)
   if (mode < 0) { const char* e = getenv("DQ_CONV_BWD_NOTMA"); mode = (e && e[0] == '1') ? 1 : 0; }
-  if (al && mode == 0 && a.L >= 256) {
+  // the pipelined kernel covers: plain conv, or RMSNorm (+ scale/shift) + SiLU epilogue; channel counts in fours
+  const bool epi_ok = !a.u || (a.g && a.act == 1);
+  if (al && mode == 0 && a.L >= 256 && epi_ok && (a.c1 & 3) == 0 && (a.c2 & 3) == 0) {
     switch (cout) {
-      case 4: return launch_fused_tma<4, K, 4, 128>(a, st);
-      case 8: return launch_fused_tma<8, K, 2, 128>(a, st);
-      case 12: return launch_fused_tma<12, K, 2, 128>(a, st);
+      case 4: return launch_fused_tma_epi<4, K, 4, 128>(a, st);
+      case 8: return launch_fused_tma_epi<8, K, 2, 128>(a, st);
+      case 12: return launch_fused_tma_epi<12, K, 2, 128>(a, st);
       default: break;
     }
   }
