@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(128) la_out_kernel(LAArgs a) {
 // Reductions over positions (Gq = Qs^T dY, dWq = dQr^T Xn) read Qs / dQr back from warp-private shared tiles in
 // the transposed role.
 template <int C>
-__global__ void __launch_bounds__(128) la_bwd_q_kernel(LAArgs a) {
+__global__ void __launch_bounds__(128, (C <= 8 ? 5 : 1)) la_bwd_q_kernel(LAArgs a) {
   using T = TC<C>;
   extern __shared__ float4 dyn_smem4[];
   float* xn_s = reinterpret_cast<float*>(dyn_smem4);   // SP * XS
@@ -593,10 +593,10 @@ __global__ void __launch_bounds__(128) la_bwd_q_kernel(LAArgs a) {
 #pragma unroll
         for (int dt = 0; dt < 4; ++dt) mma_kc<T::KC>(dqs[dt], ax, bgA[dt]);
       }
-      softmax_rows(qs, scale);
-      uint32_t rq[4][4];
-      round_tile(qs, rq);
-      store_tile16x32(scrQ, rq, g, t);
+      // q carries a (1 + 2^-11) factor: the MMA's operand truncation of q (in Gq) and of dQr = q (dQs - ts) (in dWq,
+      // d xn_q) is then unbiased without any explicit rounding instruction
+      softmax_rows(qs, scale * kTfBiasMul);
+      store_tile16x32(scrQ, reinterpret_cast<const uint32_t(&)[4][4]>(qs), g, t);
       // softmax backward: dQr = Qs * (dQs - sum_d Qs dQs / scale)
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(128) la_bwd_q_kernel(LAArgs a) {
           dqs[dt][2 * hf + 1] = qs[dt][2 * hf + 1] * (dqs[dt][2 * hf + 1] - ts);
         }
       }
-      round_tile(dqs, rq);
+      const uint32_t (&rq)[4][4] = reinterpret_cast<const uint32_t(&)[4][4]>(dqs);
       store_tile16x32(scrR, rq, g, t);
       {  // d xn_q (this head) = dQr Wq_h
         float dxn[T::CT][4];
@@ -757,7 +757,7 @@ __global__ void __launch_bounds__(128) la_bwd_combine_kernel(LAArgs a, int rows_
 
 // ------------------------------------------------------------------------------------------- backward: k path
 template <int C>
-__global__ void __launch_bounds__(128) la_bwd_kv_kernel(LAArgs a) {
+__global__ void __launch_bounds__(128, (C <= 8 ? 5 : 1)) la_bwd_kv_kernel(LAArgs a) {
   using T = TC<C>;
   extern __shared__ float4 dyn_smem4[];
   float* xn_s = reinterpret_cast<float*>(dyn_smem4);   // SP * XS
@@ -795,7 +795,9 @@ __global__ void __launch_bounds__(128) la_bwd_kv_kernel(LAArgs a) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const size_t jd = (size_t)r * kHD + h * 32 + 8 * dt + 2 * t + i;
-      cn[dt][i] = -(a.msm[jd * T::PS] * kLog2e + log2f(a.msm[jd * T::PS + 1]));  // softmax_L(k) = 2^(k log2e + cn)
+      // softmax_L(k) = 2^(k log2e + cn); the + kTfBias pre-scales ks (and d k_raw = ks (..)) by (1 + 2^-11) so that the
+      // MMA's operand truncation is unbiased without explicit rounding
+      cn[dt][i] = kTfBias - (a.msm[jd * T::PS] * kLog2e + log2f(a.msm[jd * T::PS + 1]));
       cd[dt][i] = a.sd[jd];
     }
   }
@@ -828,9 +830,8 @@ __global__ void __launch_bounds__(128) la_bwd_kv_kernel(LAArgs a) {
           }
         }
       }
-      uint32_t rk[4][4], rd[4][4];
-      round_tile(kk, rk);
-      round_tile(dks, rd);
+      const uint32_t (&rk)[4][4] = reinterpret_cast<const uint32_t(&)[4][4]>(kk);
+      const uint32_t (&rd)[4][4] = reinterpret_cast<const uint32_t(&)[4][4]>(dks);
       store_tile16x32(scrK, rd, g, t);
       {
         float dxn[T::CT][4];
