@@ -432,6 +432,10 @@ class ModelInterface(object):
             kw = {} if t is None else {"t": t[sl]}
             if hasattr(self.model, "_final_microbatch"):
                 self.model._final_microbatch = (k == n_mb - 1)
+            if hasattr(self.model, "_wgrad_defer") and n_mb > 1 and x_0.dim() == 3:
+                # mid-stage weight gradients: one GEMM per optimizer step over the K-concatenated micro-batches
+                rp = x_0.shape[1] + 2
+                self.model._wgrad_defer = (s * rp, b * rp, k == n_mb - 1)
             loss = self.train_step(
                 x_0[sl],
                 ms2_cond=None if ms2_cond is None else ms2_cond[sl],
@@ -443,6 +447,8 @@ class ModelInterface(object):
             lm = loss.mean() * w
             lm.backward()
             total = lm.detach() if total is None else total + lm.detach()
+        if hasattr(self.model, "_wgrad_defer"):
+            self.model._wgrad_defer = None
         self._allreduce_grads()
         if isinstance(self.optimizer, FusedAdamW):
             self.optimizer.step(max_grad_norm=self.max_grad_norm)

@@ -187,6 +187,8 @@ class UNet1d(nn.Module):
         # (the four 300 M mid-conv weights + mid attention projections) while the down-path backward still runs
         self.grad_ready_callback = None
         self._final_microbatch = True
+        self._wgrad_defer = None   # (padded rows before, padded rows total, is last micro-batch) or None
+        self._wgrad_stash = {}
 
     # ---------------------------------------------------------------------------------------------- layout
     def _ss_producers(self):
@@ -515,10 +517,11 @@ class UNet1d(nn.Module):
               K, taps, a_row_off, a_k_off, b_k_off, b_tap, nz=1, z_b_koff_step=0, z_c_stride=0, z_b_tap_step=0):
         offs = list(a_row_off) + [0] * (4 - len(a_row_off)) + list(a_k_off) + [0] * (4 - len(a_k_off)) \
             + list(b_k_off) + [0] * (4 - len(b_k_off)) + list(b_tap) + [0] * (4 - len(b_tap))
+        bn = self.gemm_bn if self.gemm_bn else (256 if Nn >= 256 else 128)
         N.call("dq_gemm_bf16_tn", A, a_rows, a_cols, a_ld, B, b_rows, b_cols, b_ld, b_tap_stride, b_ntaps, C, ldc,
-               bias, acc, M, Nn, K, taps, offs, nz, z_b_koff_step, z_b_tap_step, z_c_stride, self.gemm_bn)
+               bias, acc, M, Nn, K, taps, offs, nz, z_b_koff_step, z_b_tap_step, z_c_stride, bn)
 
-    gemm_bn = 128
+    gemm_bn = 0   # 0: 128 x 256 tiles when N >= 256 (measured 1043 vs 889 TFLOP/s at M = 1152), else 128 x 128
 
     def _mid_conv_fwd(self, Ap, wname, bname, b, rt):
         """Ap: bf16 padded [Mp][N] -> fp32 padded [Mp][N] = conv3 over RT (+bias)."""
@@ -540,17 +543,34 @@ class UNet1d(nn.Module):
         return dX
 
     def _mid_conv_wgrad(self, dUp, Ap, wname, b, rt):
-        """dW[t][co][ci] += sum_m' dU[m'][co] * A[m' + t - 1][ci]   (both padded bf16 [Mp][N])."""
+        """dW[t][co][ci] += sum_m' dU[m'][co] * A[m' + t - 1][ci]   (both padded bf16 [Mp][N]).
+
+        With gradient accumulation over micro-batches (`_wgrad_defer = (rows_before, rows_total, is_last)`, set by
+        ModelInterface._train_one_batch) the transposed operands of every micro-batch are appended along K and ONE
+        GEMM per weight runs in the last micro-batch: the 1.2 GB fp32 read-modify-write of dW happens once per
+        optimizer step instead of once per micro-batch."""
         Nm = self.mid_channels
         Mp = b * (rt + 2)
-        ld = _ceil8(Mp)
-        dUT = self._empty(Nm, ld, dtype=torch.bfloat16)
-        AT3 = self._empty(3, Nm, ld, dtype=torch.bfloat16)  # AT3[t][ci][m'] = A[m' + t - 1][ci]
-        N.call("dq_transpose_bf16", dUp, dUT, Mp, Nm, ld, 0)
+        plan = self._wgrad_defer
+        if plan is None:
+            off, total, last = 0, Mp, True
+            ld = _ceil8(Mp)
+            dUT = self._empty(Nm, ld, dtype=torch.bfloat16)
+            AT3 = self._empty(3, Nm, ld, dtype=torch.bfloat16)  # AT3[t][ci][m'] = A[m' + t - 1][ci]
+        else:
+            off, total, last = plan
+            ld = _ceil8(total)
+            st = self._wgrad_stash.get(wname)
+            if st is None or st[0].shape[1] != ld or st[0].device != dUp.device:
+                st = (self._empty(Nm, ld, dtype=torch.bfloat16), self._empty(3, Nm, ld, dtype=torch.bfloat16))
+                self._wgrad_stash[wname] = st
+            dUT, AT3 = st
+        N.call("dq_transpose_bf16", dUp, dUT.data_ptr() + 2 * off, Mp, Nm, ld, 0)
         for t in range(3):
-            N.call("dq_transpose_bf16", Ap, AT3[t], Mp, Nm, ld, t - 1)
-        self._gemm(dUT, Nm, Mp, ld, AT3, Nm, Mp, ld, Nm * ld, 3, self._gw(wname), Nm, None, 1, Nm, Nm, Mp, 1,
-                   (0,), (0,), (0,), (0,), nz=3, z_b_tap_step=1, z_c_stride=Nm * Nm)
+            N.call("dq_transpose_bf16", Ap, AT3[t].data_ptr() + 2 * off, Mp, Nm, ld, t - 1)
+        if last:
+            self._gemm(dUT, Nm, total, ld, AT3, Nm, total, ld, Nm * ld, 3, self._gw(wname), Nm, None, 1, Nm, Nm, total, 1,
+                       (0,), (0,), (0,), (0,), nz=3, z_b_tap_step=1, z_c_stride=Nm * Nm)
 
     def _mid_block_fwd(self, pre, X, b, rt, save):
         """X fp32 [M][N] -> fp32 [M][N]; ResnetBlock(N, N) with identity skip (unet1d.py:1029/1058)."""

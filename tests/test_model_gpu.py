@@ -76,6 +76,32 @@ def test_train_step_loss_and_gradients_match_reference_golden():
         assert _cos(delta_got, delta_ref) > 0.99, k
 
 
+def test_micro_batched_step_matches_single_pass():
+    """Gradient accumulation over micro-batches (with the K-concatenated mid-stage weight-gradient GEMM that runs once
+    per optimizer step) must give the same gradients as one pass over the whole batch."""
+    from dquartic.model.model import DDIMDiffusionModel
+
+    g = golden("train_tiny.npz")
+    x0, c2, c1 = (torch.from_numpy(g[k]).cuda() for k in ("x0", "ms2_cond", "ms1_cond"))
+    noise = torch.from_numpy(g["noise"]).cuda()
+    t = torch.from_numpy(g["t"]).cuda()
+    x0, c2, c1, noise, t = (torch.cat([v, v.flip(0)]) for v in (x0, c2, c1, noise, t))   # batch 4
+    grads = []
+    for mb in (None, 1, 3):
+        net, _ = make_net()
+        net.train()
+        d = DDIMDiffusionModel(net, device="cuda")
+        d._prepare_training(0.0)           # lr 0: the step leaves the parameters alone, gradients stay inspectable
+        d.micro_batch = mb
+        loss = d._train_one_batch(x0, c2, c1, noise=(noise + 1) * 0.5, t=t)
+        grads.append((loss, net.flat_grads().clone()))
+        assert net._wgrad_defer is None
+    for loss, gflat in grads[1:]:
+        assert abs(loss - grads[0][0]) < 1e-5 * abs(grads[0][0])
+        assert rel_err(gflat, grads[0][1]) < 5e-3
+        assert _cos(gflat, grads[0][1]) > 0.99999
+
+
 def test_ddim_sampling_matches_reference_golden():
     from dquartic.model.model import DDIMDiffusionModel
 
