@@ -402,14 +402,17 @@ __device__ __forceinline__ float cf_dsilu(float z) {
 }
 
 // EPI = false: plain conv (du = dy).  EPI = true: RMSNorm (g) + optional per-sample scale/shift + SiLU epilogue.
-template <int COUT, int K, int P, int NT, bool EPI>
+// BULK = true: rows are 16-byte aligned, one cp.async.bulk per row.  BULK = false: any alignment (L % 4 != 0, i.e. the
+// L = 1250 / 625 levels): every thread stages its share of the tile with 4-byte cp.async (LDGSTS) that arrive on the same
+// mbarrier; everything downstream of the staging is identical.
+template <int COUT, int K, int P, int NT, bool EPI, bool BULK>
 __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs a) {
   constexpr int TL = NT * P;
   constexpr int TS = TL + 36;
   constexpr int H = (K - 1) / 2;
   constexpr int NW = NT / 32;
   constexpr int DYR = EPI ? 2 * COUT : COUT;             // dy rows, [u rows]
-  static_assert(P == 2 || P == 4, "P");
+  static_assert(P == 1 || P == 2 || P == 4, "P");
   extern __shared__ float4 dyn_smem4[];
   const int cin = a.c1 + a.c2;                           // multiple of 4 (checked by the launcher), as is c1
   const int rows = DYR + cin;
@@ -423,8 +426,8 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
   const uint32_t bar0 = cf_smem_u32(bars), bar1 = bar0 + 8;
 
   if (tid == 0) {
-    cf_mbar_init(bar0, 1);
-    cf_mbar_init(bar1, 1);
+    cf_mbar_init(bar0, BULK ? 1 : NT);
+    cf_mbar_init(bar1, BULK ? 1 : NT);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < COUT * cin * 4; i += NT) {
@@ -432,13 +435,36 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
     w_s[i] = (k < K) ? a.w[(size_t)pc * K + k] : 0.f;
   }
   for (int i = tid; i < COUT * cin * K; i += NT) dw_s[i] = 0.f;
+  // stage slots that no copy ever fills (beyond a row end) must hold finite values: 0 * stale stays 0
+  for (int i = tid; i < 2 * stage_floats; i += NT) stage0[i] = 0.f;
   __syncthreads();
 
   const int t_begin = blockIdx.x * a.tiles_per_cta, t_end = min(a.total_tiles, t_begin + a.tiles_per_cta);
   const int n_tiles = t_end - t_begin;
 
-  // one lane per row issues that row's bulk copy; lane 0 posts the expected byte count first
+  // BULK: one lane per row issues that row's bulk copy; lane 0 posts the expected byte count first
   auto issue = [&](int tile, int s) {
+    if (!BULK) {
+      const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
+      const int l_lo = max(0, tl0 - 4), l_hi = min(a.L, tl0 + TL + 4);
+      const int w = l_hi - l_lo, doff = l_lo - (tl0 - 4);
+      float* st = stage0 + s * stage_floats;
+      for (int row = 0; row < rows; ++row) {
+        const float* src;
+        if (row < COUT) src = a.dy + ((size_t)r * COUT + row) * a.L;
+        else if (row < DYR) src = a.u + ((size_t)r * COUT + (row - COUT)) * a.L;
+        else {
+          const int ci = row - DYR;
+          src = (ci < a.c1) ? a.x1 + ((size_t)r * a.c1 + ci) * a.L : a.x2 + ((size_t)r * a.c2 + (ci - a.c1)) * a.L;
+        }
+        src += l_lo;
+        const uint32_t dst = cf_smem_u32(st + row * TS + doff);
+        for (int e = tid; e < w; e += NT)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (uint32_t)e), "l"(src + e) : "memory");
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(s ? bar1 : bar0) : "memory");
+      return;
+    }
     if (tid < 32) {
       const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
       const int l_lo = max(0, tl0 - 4), l_hi = min(a.L, tl0 + TL + 4);
@@ -566,16 +592,19 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
         float dyv[P][COUT], uv[P][COUT];
 #pragma unroll
         for (int c = 0; c < COUT; ++c) {
-          if (P == 4) {
+          if constexpr (P == 4) {
             const float4 d4 = *reinterpret_cast<const float4*>(du_s + c * TS + idx);
             dyv[0][c] = d4.x; dyv[1][c] = d4.y; dyv[2][c] = d4.z; dyv[3][c] = d4.w;
             const float4 u4 = *reinterpret_cast<const float4*>(u_t + c * TS + idx);
             uv[0][c] = u4.x; uv[1][c] = u4.y; uv[2][c] = u4.z; uv[3][c] = u4.w;
-          } else {
+          } else if constexpr (P == 2) {
             const float2 d2 = *reinterpret_cast<const float2*>(du_s + c * TS + idx);
-            dyv[0][c] = d2.x; dyv[1][c] = d2.y;
+            dyv[0][c] = d2.x; dyv[P - 1][c] = d2.y;
             const float2 u2 = *reinterpret_cast<const float2*>(u_t + c * TS + idx);
-            uv[0][c] = u2.x; uv[1][c] = u2.y;
+            uv[0][c] = u2.x; uv[P - 1][c] = u2.y;
+          } else {
+            dyv[0][c] = du_s[c * TS + idx];
+            uv[0][c] = u_t[c * TS + idx];
           }
         }
         if (!ok) {
@@ -588,8 +617,9 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
         for (int i = 0; i < P; ++i) du_at(dyv[i], uv[i], true);
 #pragma unroll
         for (int c = 0; c < COUT; ++c) {
-          if (P == 4) *reinterpret_cast<float4*>(du_s + c * TS + idx) = make_float4(dyv[0][c], dyv[1][c], dyv[2][c], dyv[3][c]);
-          else *reinterpret_cast<float2*>(du_s + c * TS + idx) = make_float2(dyv[0][c], dyv[1][c]);
+          if constexpr (P == 4) *reinterpret_cast<float4*>(du_s + c * TS + idx) = make_float4(dyv[0][c], dyv[1][c], dyv[2][c], dyv[3][c]);
+          else if constexpr (P == 2) *reinterpret_cast<float2*>(du_s + c * TS + idx) = make_float2(dyv[0][c], dyv[P - 1][c]);
+          else du_s[c * TS + idx] = dyv[0][c];
         }
       }
       if (H > 0 && (tid == 0 || tid == NT - 1)) {   // halo positions tl0 - 1 and tl0 + TL (no accumulation)
@@ -612,14 +642,18 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
       const bool ok = tl0 + P * tid < a.L;
 #pragma unroll
       for (int c = 0; c < COUT; ++c) {
-        if (P == 4) {
+        if constexpr (P == 4) {
           float4 d4 = *reinterpret_cast<const float4*>(du_s + c * TS + idx);
           if (!ok) { d4 = make_float4(0.f, 0.f, 0.f, 0.f); *reinterpret_cast<float4*>(du_s + c * TS + idx) = d4; }
           accB[c] += (d4.x + d4.y) + (d4.z + d4.w);
-        } else {
+        } else if constexpr (P == 2) {
           float2 d2 = *reinterpret_cast<const float2*>(du_s + c * TS + idx);
           if (!ok) { d2 = make_float2(0.f, 0.f); *reinterpret_cast<float2*>(du_s + c * TS + idx) = d2; }
           accB[c] += d2.x + d2.y;
+        } else {
+          float d1 = du_s[c * TS + idx];
+          if (!ok) { d1 = 0.f; du_s[c * TS + idx] = 0.f; }
+          accB[c] += d1;
         }
       }
       if (H > 0 && tid < COUT) {
@@ -660,9 +694,10 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
         for (int co = 0; co < COUT; ++co) {
           float dwin[P + 2];   // du[co][pos - 1 .. pos + P]
           const float* dr = du_s + co * TS + 4 + P * tid;
-          if (P == 4) { const float4 m = *reinterpret_cast<const float4*>(dr); dwin[1] = m.x; dwin[2] = m.y; dwin[3] = m.z; dwin[4] = m.w; }
-          else { const float2 m = *reinterpret_cast<const float2*>(dr); dwin[1] = m.x; dwin[2] = m.y; }
-          if (K == 3) { dwin[0] = dr[-1]; dwin[P + 1] = dr[P]; }
+          if constexpr (P == 4) { const float4 m = *reinterpret_cast<const float4*>(dr); dwin[1] = m.x; dwin[2] = m.y; dwin[3] = m.z; dwin[P] = m.w; }
+          else if constexpr (P == 2) { const float2 m = *reinterpret_cast<const float2*>(dr); dwin[1] = m.x; dwin[P] = m.y; }
+          else dwin[1] = dr[0];
+          if constexpr (K == 3) { dwin[0] = dr[-1]; dwin[P + 1] = dr[P]; }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 w4 = *reinterpret_cast<const float4*>(w_s + (co * cin + cb + j) * 4);
@@ -677,16 +712,26 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float* d = dst + (size_t)j * a.L;
-            if (P == 4) {
-              float4 v = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+            if constexpr (BULK && P == 4) {
+              float4 v = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][P - 1]);
               if (add) { const float4 q = __ldg(reinterpret_cast<const float4*>(add + (size_t)j * a.L)); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
               if (accf) { const float4 q = *reinterpret_cast<const float4*>(d); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
               *reinterpret_cast<float4*>(d) = v;
-            } else {
-              float2 v = make_float2(acc[j][0], acc[j][1]);
+            } else if constexpr (BULK && P == 2) {
+              float2 v = make_float2(acc[j][0], acc[j][P - 1]);
               if (add) { const float2 q = __ldg(reinterpret_cast<const float2*>(add + (size_t)j * a.L)); v.x += q.x; v.y += q.y; }
               if (accf) { const float2 q = *reinterpret_cast<const float2*>(d); v.x += q.x; v.y += q.y; }
               *reinterpret_cast<float2*>(d) = v;
+            } else {   // unaligned rows: scalar accesses (positions beyond L are masked individually)
+#pragma unroll
+              for (int i = 0; i < P; ++i) {
+                if (l + i < a.L) {
+                  float v = acc[j][i];
+                  if (add) v += __ldg(add + (size_t)j * a.L + i);
+                  if (accf) v += d[i];
+                  d[i] = v;
+                }
+              }
             }
           }
         }
@@ -699,7 +744,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
       for (int q = q_begin; q < q_end; q += 4) {
         const float4 xm = *reinterpret_cast<const float4*>(xr + q);
         float x6[6] = {0.f, xm.x, xm.y, xm.z, xm.w, 0.f};
-        if (K == 3) { x6[0] = xr[q - 1]; x6[5] = xr[q + 4]; }
+        if constexpr (K == 3) { x6[0] = xr[q - 1]; x6[5] = xr[q + 4]; }
 #pragma unroll
         for (int co = 0; co < COUT; ++co) {
           const float4 d4 = *reinterpret_cast<const float4*>(du_s + co * TS + 4 + q);
@@ -734,7 +779,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
   for (int i = tid; i < COUT * cin * K; i += NT) atomicAdd(a.dw + i, dw_s[i]);
 }
 
-template <int COUT, int K, int P, int NT, bool EPI>
+template <int COUT, int K, int P, int NT, bool EPI, bool BULK>
 static int launch_fused_tma(ConvBwdFusedArgs a, cudaStream_t st) {
   constexpr int TL = NT * P, TS = TL + 36, NW = NT / 32;
   const int cin = a.c1 + a.c2;
@@ -743,7 +788,7 @@ static int launch_fused_tma(ConvBwdFusedArgs a, cudaStream_t st) {
   a.total_tiles = a.tiles_per_row * a.R;
   size_t smem = sizeof(float) * ((size_t)2 * rows * TS + (size_t)COUT * cin * 4 + (size_t)COUT * cin * K + NW * 2 * COUT) + 16;
   if (smem > 220 * 1024) return -6;
-  auto kern = conv_bwd_fused_tma_kernel<COUT, K, P, NT, EPI>;
+  auto kern = conv_bwd_fused_tma_kernel<COUT, K, P, NT, EPI, BULK>;
   static int sm_count = 0;
   if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -757,9 +802,9 @@ static int launch_fused_tma(ConvBwdFusedArgs a, cudaStream_t st) {
   DQ_LAUNCH_CHECK();
   return 0;
 }
-template <int COUT, int K, int P, int NT>
+template <int COUT, int K, int P, int NT, bool BULK>
 static int launch_fused_tma_epi(const ConvBwdFusedArgs& a, cudaStream_t st) {
-  return a.u ? launch_fused_tma<COUT, K, P, NT, true>(a, st) : launch_fused_tma<COUT, K, P, NT, false>(a, st);
+  return a.u ? launch_fused_tma<COUT, K, P, NT, true, BULK>(a, st) : launch_fused_tma<COUT, K, P, NT, false, BULK>(a, st);
 }
 
 template <int COUT, int K, int P, int VEC>
@@ -793,12 +838,23 @@ static int dispatch_fused(const ConvBwdFusedArgs& a, int cout, cudaStream_t st) 
   if (mode < 0) { const char* e = getenv("DQ_CONV_BWD_NOTMA"); mode = (e && e[0] == '1') ? 1 : 0; }
   // the pipelined kernel covers: plain conv, or RMSNorm (+ scale/shift) + SiLU epilogue; channel counts in fours
   const bool epi_ok = !a.u || (a.g && a.act == 1);
-  if (al && mode == 0 && a.L >= 256 && epi_ok && (a.c1 & 3) == 0 && (a.c2 & 3) == 0) {
-    switch (cout) {
-      case 4: return launch_fused_tma_epi<4, K, 4, 128>(a, st);
-      case 8: return launch_fused_tma_epi<8, K, 2, 128>(a, st);
-      case 12: return launch_fused_tma_epi<12, K, 2, 128>(a, st);
-      default: break;
+  if (mode == 0 && a.L >= 128 && epi_ok && (a.c1 & 3) == 0 && (a.c2 & 3) == 0) {
+    if (al) {
+      switch (cout) {
+        case 4: return launch_fused_tma_epi<4, K, 4, 128, true>(a, st);
+        case 8: return launch_fused_tma_epi<8, K, 2, 128, true>(a, st);
+        case 12: return launch_fused_tma_epi<12, K, 2, 128, true>(a, st);
+        case 16: return launch_fused_tma_epi<16, K, 1, 128, true>(a, st);
+        default: break;
+      }
+    } else {
+      switch (cout) {
+        case 4: return launch_fused_tma_epi<4, K, 4, 128, false>(a, st);
+        case 8: return launch_fused_tma_epi<8, K, 2, 128, false>(a, st);
+        case 12: return launch_fused_tma_epi<12, K, 1, 128, false>(a, st);
+        case 16: return launch_fused_tma_epi<16, K, 1, 128, false>(a, st);
+        default: break;
+      }
     }
   }
   switch (cout) {
@@ -825,12 +881,12 @@ struct ConvFwdTmaArgs {
   int c1, c2, R, L, rows_per_sample, ss_stride, act, tiles_per_row, total_tiles, tiles_per_cta;
 };
 
-template <int COUT, int K, int P, int NT>
+template <int COUT, int K, int P, int NT, bool BULK>
 __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
   constexpr int TL = NT * P;
   constexpr int TS = TL + 36;
   constexpr int H = (K - 1) / 2;
-  static_assert(P == 2 || P == 4, "P");
+  static_assert(P == 1 || P == 2 || P == 4, "P");
   static_assert(COUT % 4 == 0, "COUT");
   extern __shared__ float4 dyn_smem4[];
   const int cin = a.c1 + a.c2;
@@ -843,8 +899,8 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
   const int tid = threadIdx.x;
   const uint32_t bar0 = cf_smem_u32(bars), bar1 = bar0 + 8;
   if (tid == 0) {
-    cf_mbar_init(bar0, 1);
-    cf_mbar_init(bar1, 1);
+    cf_mbar_init(bar0, BULK ? 1 : NT);
+    cf_mbar_init(bar1, BULK ? 1 : NT);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < cin * K * COUT; i += NT) {
@@ -856,6 +912,24 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
   const int n_tiles = t_end - t_begin;
 
   auto issue = [&](int tile, int s) {
+    if (!BULK) {   // any alignment: 4-byte cp.async from every thread, arriving on the same mbarrier
+      const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
+      const int l_lo = max(0, tl0 - 4), l_hi = min(a.L, tl0 + TL + 4);
+      const int w = l_hi - l_lo, doff = l_lo - (tl0 - 4);
+      float* st = stage0 + s * stage_floats;
+      for (int row = 0; row < rows; ++row) {
+        const float* src;
+        if (row < a.c1) src = a.x1 + ((size_t)r * a.c1 + row) * a.L;
+        else if (row < cin) src = a.x2 + ((size_t)r * a.c2 + (row - a.c1)) * a.L;
+        else src = a.res + ((size_t)r * COUT + (row - cin)) * a.L;
+        src += l_lo;
+        const uint32_t dst = cf_smem_u32(st + row * TS + doff);
+        for (int e = tid; e < w; e += NT)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (uint32_t)e), "l"(src + e) : "memory");
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(s ? bar1 : bar0) : "memory");
+      return;
+    }
     if (tid < 32) {
       const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
       const int l_lo = max(0, tl0 - 4), l_hi = min(a.L, tl0 + TL + 4);
@@ -907,9 +981,10 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
     for (int ci = 0; ci < cin; ++ci) {
       float xw[P + 2];
       const float* xr = x_t + ci * TS + 4 + P * tid;
-      if (P == 4) { const float4 m = *reinterpret_cast<const float4*>(xr); xw[1] = m.x; xw[2] = m.y; xw[3] = m.z; xw[4] = m.w; }
-      else { const float2 m = *reinterpret_cast<const float2*>(xr); xw[1] = m.x; xw[2] = m.y; }
-      if (K == 3) { xw[0] = xr[-1]; xw[P + 1] = xr[P]; }
+      if constexpr (P == 4) { const float4 m = *reinterpret_cast<const float4*>(xr); xw[1] = m.x; xw[2] = m.y; xw[3] = m.z; xw[P] = m.w; }
+      else if constexpr (P == 2) { const float2 m = *reinterpret_cast<const float2*>(xr); xw[1] = m.x; xw[P] = m.y; }
+      else xw[1] = xr[0];
+      if constexpr (K == 3) { xw[0] = xr[-1]; xw[P + 1] = xr[P]; }
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const float4* wp = reinterpret_cast<const float4*>(w_s + (ci * K + k) * COUT);
@@ -932,8 +1007,12 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
       if (a.u) {
 #pragma unroll
         for (int c = 0; c < COUT; ++c) {
-          if (P == 4) *reinterpret_cast<float4*>(a.u + base + (size_t)c * a.L) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
-          else *reinterpret_cast<float2*>(a.u + base + (size_t)c * a.L) = make_float2(acc[0][c], acc[1][c]);
+          if constexpr (BULK && P == 4) *reinterpret_cast<float4*>(a.u + base + (size_t)c * a.L) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[P - 1][c]);
+          else if constexpr (BULK && P == 2) *reinterpret_cast<float2*>(a.u + base + (size_t)c * a.L) = make_float2(acc[0][c], acc[P - 1][c]);
+          else {
+#pragma unroll
+            for (int i = 0; i < P; ++i) if (l + i < a.L) a.u[base + (size_t)c * a.L + i] = acc[i][c];
+          }
         }
       }
       float gs[COUT], sh[COUT];
@@ -963,8 +1042,12 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
       }
 #pragma unroll
       for (int c = 0; c < COUT; ++c) {
-        if (P == 4) *reinterpret_cast<float4*>(a.y + base + (size_t)c * a.L) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
-        else *reinterpret_cast<float2*>(a.y + base + (size_t)c * a.L) = make_float2(acc[0][c], acc[1][c]);
+        if constexpr (BULK && P == 4) *reinterpret_cast<float4*>(a.y + base + (size_t)c * a.L) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[P - 1][c]);
+        else if constexpr (BULK && P == 2) *reinterpret_cast<float2*>(a.y + base + (size_t)c * a.L) = make_float2(acc[0][c], acc[P - 1][c]);
+        else {
+#pragma unroll
+          for (int i = 0; i < P; ++i) if (l + i < a.L) a.y[base + (size_t)c * a.L + i] = acc[i][c];
+        }
       }
     }
     __syncthreads();   // everyone is done with stage s
@@ -972,7 +1055,7 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
   }
 }
 
-template <int COUT, int K, int P, int NT>
+template <int COUT, int K, int P, int NT, bool BULK>
 static int launch_fwd_tma(ConvFwdTmaArgs a, cudaStream_t st) {
   constexpr int TL = NT * P, TS = TL + 36;
   const int cin = a.c1 + a.c2;
@@ -981,7 +1064,7 @@ static int launch_fwd_tma(ConvFwdTmaArgs a, cudaStream_t st) {
   a.total_tiles = a.tiles_per_row * a.R;
   size_t smem = sizeof(float) * ((size_t)2 * rows * TS + (size_t)cin * K * COUT) + 16;
   if (smem > 220 * 1024) return -6;
-  auto kern = conv_fwd_tma_kernel<COUT, K, P, NT>;
+  auto kern = conv_fwd_tma_kernel<COUT, K, P, NT, BULK>;
   static int sm_count = 0;
   if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -996,31 +1079,36 @@ static int launch_fwd_tma(ConvFwdTmaArgs a, cudaStream_t st) {
   return 0;
 }
 
-// Returns 1 if the pipelined kernel took the call, 0 if the shape / alignment is not eligible, < 0 on error.
+// Returns 1 if the pipelined kernel took the call, 0 if the shape is not eligible, < 0 on error.
 int conv_fwd_tma_try(const float* x1, int c1, const float* x2, int c2, const float* w, const float* bias, int cout, int K,
                      const float* g, const float* ss, int ss_stride, int act, const float* res, float* u, float* y, int R,
                      int L, int rows_per_sample, cudaStream_t st) {
   static int mode = -1;   // DQ_CONV_FWD_NOTMA=1 forces the plain-load kernel (cross-check)
   if (mode < 0) { const char* e = getenv("DQ_CONV_FWD_NOTMA"); mode = (e && e[0] == '1') ? 1 : 0; }
-  if (mode == 1 || (K != 1 && K != 3) || L % 4 != 0 || L < 256 || c1 + c2 > 64) return 0;
-  if ((((size_t)x1 | (size_t)x2 | (size_t)res | (size_t)u | (size_t)y) & 15) != 0) return 0;
+  if (mode == 1 || (K != 1 && K != 3) || L < 128 || c1 + c2 > 64) return 0;
+  const bool al = (L % 4 == 0) && ((((size_t)x1 | (size_t)x2 | (size_t)res | (size_t)u | (size_t)y) & 15) == 0);
   ConvFwdTmaArgs a{x1, x2, w, bias, g, ss, res, u, y, c1, c2, R, L, rows_per_sample, ss_stride, act, 0, 0, 0};
   int rc;
+#define DQ_FWD_CASE(CO, KK, PA, PU) \
+  case CO: rc = al ? launch_fwd_tma<CO, KK, PA, 128, true>(a, st) : launch_fwd_tma<CO, KK, PU, 128, false>(a, st); break;
   if (K == 3) {
     switch (cout) {
-      case 4: rc = launch_fwd_tma<4, 3, 4, 128>(a, st); break;
-      case 8: rc = launch_fwd_tma<8, 3, 4, 128>(a, st); break;
-      case 12: rc = launch_fwd_tma<12, 3, 2, 128>(a, st); break;
+      DQ_FWD_CASE(4, 3, 4, 4)
+      DQ_FWD_CASE(8, 3, 4, 2)
+      DQ_FWD_CASE(12, 3, 2, 1)
+      DQ_FWD_CASE(16, 3, 2, 1)
       default: return 0;
     }
   } else {
     switch (cout) {
-      case 4: rc = launch_fwd_tma<4, 1, 4, 128>(a, st); break;
-      case 8: rc = launch_fwd_tma<8, 1, 4, 128>(a, st); break;
-      case 12: rc = launch_fwd_tma<12, 1, 2, 128>(a, st); break;
+      DQ_FWD_CASE(4, 1, 4, 4)
+      DQ_FWD_CASE(8, 1, 4, 2)
+      DQ_FWD_CASE(12, 1, 2, 1)
+      DQ_FWD_CASE(16, 1, 2, 1)
       default: return 0;
     }
   }
+#undef DQ_FWD_CASE
   return rc == 0 ? 1 : rc;
 }
 
