@@ -142,3 +142,100 @@ DQ_API int dq_ncl_nlc(const float* in, float* out, int B, int C, int L, int reve
   DQ_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------- resampling glue
+// The backward passes of Upsample (nearest x2 + Conv1d k3, unet1d.py:93-96) and Downsample (Conv1d k4 s2 p1, 110) run
+// through the fused stride-1 backward kernel (conv_fused.cu) on re-indexed tensors:
+//   up  : x_up[2j] = x_up[2j+1] = x[j];  dx[j] = dx_up[2j] + dx_up[2j+1]
+//   down: the k4/s2 conv is a k3/s1 conv over the 2C-channel half-rate tensor [x_even; x_odd] with weights
+//         even channel c: taps (0, w1, w3), odd channel c: taps (w0, w2, 0)
+namespace dq {
+__global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ x, float* __restrict__ y, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    reinterpret_cast<float2*>(y)[i] = make_float2(v, v);
+  }
+}
+__global__ void __launch_bounds__(256) fold2x_kernel(const float* __restrict__ d, float* __restrict__ dx, long n, int acc) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float2 v = reinterpret_cast<const float2*>(d)[i];
+    const float s = v.x + v.y;
+    dx[i] = acc ? dx[i] + s : s;
+  }
+}
+// x (rows, L) -> y viewed as (R, 2C, L/2): row = r*C + c goes to rows r*2C + c (even samples) and r*2C + C + c (odd)
+__global__ void __launch_bounds__(256) s2d_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int Lh, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long row = i / Lh;
+    const int j = (int)(i - row * Lh);
+    const long r = row / C;
+    const int c = (int)(row - r * C);
+    const float2 v = reinterpret_cast<const float2*>(x)[i];
+    y[((r * 2 * C + c)) * Lh + j] = v.x;
+    y[((r * 2 * C + C + c)) * Lh + j] = v.y;
+  }
+}
+__global__ void __launch_bounds__(256) d2s_kernel(const float* __restrict__ d, float* __restrict__ dx, int C, int Lh, long n, int acc) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long row = i / Lh;
+    const int j = (int)(i - row * Lh);
+    const long r = row / C;
+    const int c = (int)(row - r * C);
+    float2 v = make_float2(d[((r * 2 * C + c)) * Lh + j], d[((r * 2 * C + C + c)) * Lh + j]);
+    float2* dst = reinterpret_cast<float2*>(dx) + i;
+    if (acc) { const float2 o = *dst; v.x += o.x; v.y += o.y; }
+    *dst = v;
+  }
+}
+// w4 (co, ci, 4) <-> w3 (co, 2ci, 3).  dir = 0: w3 = pack(w4);  dir = 1: w4 += unpack(w3)  (gradient)
+__global__ void down_w_kernel(float* __restrict__ w4, float* __restrict__ w3, int co, int ci, int dir) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= co * ci) return;
+  const int o = i / ci, c = i - o * ci;
+  float* a = w4 + (size_t)i * 4;
+  float* e = w3 + ((size_t)o * 2 * ci + c) * 3;        // even-sample channel c
+  float* d = w3 + ((size_t)o * 2 * ci + ci + c) * 3;   // odd-sample channel c
+  if (dir == 0) {
+    e[0] = 0.f; e[1] = a[1]; e[2] = a[3];
+    d[0] = a[0]; d[1] = a[2]; d[2] = 0.f;
+  } else {
+    a[0] += d[0]; a[1] += e[1]; a[2] += d[1]; a[3] += e[2];
+  }
+}
+static inline unsigned ew_grid(long n) { long g = (n + 255) / 256; return (unsigned)(g > 148L * 16 ? 148L * 16 : g); }
+}  // namespace dq
+
+DQ_API int dq_upsample2x(const float* x, float* y, long n, void* stream) {
+  if (n <= 0) return 0;
+  dq::upsample2x_kernel<<<dq::ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+DQ_API int dq_fold2x(const float* d, float* dx, long n, int acc, void* stream) {
+  if (n <= 0) return 0;
+  dq::fold2x_kernel<<<dq::ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d, dx, n, acc);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+DQ_API int dq_s2d(const float* x, float* y, int R, int C, int L, void* stream) {
+  if (L & 1) return -2;
+  const long n = (long)R * C * (L / 2);
+  if (n <= 0) return 0;
+  dq::s2d_kernel<<<dq::ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, y, C, L / 2, n);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+DQ_API int dq_d2s(const float* d, float* dx, int R, int C, int L, int acc, void* stream) {
+  if (L & 1) return -2;
+  const long n = (long)R * C * (L / 2);
+  if (n <= 0) return 0;
+  dq::d2s_kernel<<<dq::ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d, dx, C, L / 2, n, acc);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+DQ_API int dq_down_w(float* w4, float* w3, int co, int ci, int dir, void* stream) {
+  if (co * ci <= 0) return 0;
+  dq::down_w_kernel<<<(unsigned)((co * ci + 127) / 128), 128, 0, (cudaStream_t)stream>>>(w4, w3, co, ci, dir);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}

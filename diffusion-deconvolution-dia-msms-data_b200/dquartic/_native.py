@@ -27,6 +27,11 @@ _SIGS = {
     "dq_conv1d_bwd_weight": ("ppipipippiiiiiiiiis", 1),
     "dq_conv_bwd_fused": ("ppppiipipipppipippppiiiiis", 1),
     "dq_sample_dot": ("ppppilis", 1),
+    "dq_upsample2x": ("ppls", 1),
+    "dq_fold2x": ("pplis", 1),
+    "dq_s2d": ("ppiiis", 1),
+    "dq_d2s": ("ppiiiis", 1),
+    "dq_down_w": ("ppiiis", 1),
     "dq_linattn_fwd": ("pppppppppppiiis", 3),
     "dq_linattn_bwd": ("pppppppppppppppppppiiis", 3),
     "dq_time_embed": ("ppiifs", 1),

@@ -405,6 +405,10 @@ class UNet1d(nn.Module):
         if K in (1, 3) and stride == 1 and up == 1 and in_ss is None:
             return self._conv_bwd_fused(du, None, None, None, ACT_NONE, x1, x2, wname, bname, K, need_dx1, need_dx2,
                                         dx1, dx2, None, rps)
+        if K == 3 and stride == 1 and up == 2 and x2 is None and in_ss is None:
+            return self._upconv_bwd(du, x1, wname, bname, need_dx1, dx1, rps), None
+        if K == 4 and stride == 2 and pad == 1 and up == 1 and x2 is None and in_ss is None and x1.shape[2] % 2 == 0:
+            return self._downconv_bwd(du, x1, wname, bname, need_dx1, dx1, rps), None
         R, cout, Lout = du.shape
         c1, Lin = x1.shape[1], x1.shape[2]
         c2 = x2.shape[1] if x2 is not None else 0
@@ -421,6 +425,44 @@ class UNet1d(nn.Module):
             N.call("dq_conv1d_bwd_data", du, self._w(wname), dx1 if need_dx1 else None, c1, acc1,
                    dx2 if (need_dx2 and c2) else None, c2, acc2, cout, K, stride, pad, up, R, Lin, Lout)
         return dx1, dx2
+
+    def _upconv_bwd(self, du, x, wname, bname, need_dx, dx, rps):
+        """Backward of Upsample = nearest x2 + Conv1d(k3) (unet1d.py:93-96) through the fused stride-1 kernel: the
+        upsampled input is rebuilt (never saved), d x_up is folded back pairwise."""
+        R, c, Lh = x.shape
+        xup = self._empty(R, c, 2 * Lh)
+        N.call("dq_upsample2x", x, xup, x.numel())
+        dxup, _ = self._conv_bwd_fused(du, None, None, None, ACT_NONE, xup, None, wname, bname, 3, need_dx1=need_dx, rps=rps)
+        if not need_dx:
+            return None
+        acc = 1 if dx is not None else 0
+        if dx is None:
+            dx = self._empty(R, c, Lh)
+        N.call("dq_fold2x", dxup, dx, x.numel(), acc)
+        return dx
+
+    def _downconv_bwd(self, du, x, wname, bname, need_dx, dx, rps):
+        """Backward of Downsample = Conv1d(k4, s2, p1) (unet1d.py:110) as a k3/s1 conv over the space-to-depth input
+        [x_even; x_odd] with re-packed weights (csrc/small.cu)."""
+        R, c, L = x.shape
+        cout = du.shape[1]
+        Lh = L // 2
+        xs = self._empty(R, 2 * c, Lh)
+        N.call("dq_s2d", x, xs, R, c, L)
+        w3 = self._empty(cout, 2 * c, 3)
+        dw3 = self._zeros(cout, 2 * c, 3)
+        N.call("dq_down_w", self._w(wname), w3, cout, c, 0)
+        dxs = self._empty(R, 2 * c, Lh) if need_dx else None
+        N.call("dq_conv_bwd_fused", du, None, None, None, 0, ACT_NONE, xs, 2 * c, None, 0, w3, None, dxs, 0, None, 0,
+               dw3, self._gw(bname) if bname else None, None, None, cout, 3, R, Lh, rps)
+        N.call("dq_down_w", self._gw(wname), dw3, cout, c, 1)
+        if not need_dx:
+            return None
+        acc = 1 if dx is not None else 0
+        if dx is None:
+            dx = self._empty(R, c, L)
+        N.call("dq_d2s", dxs, dx, R, c, L, acc)
+        return dx
 
     def _conv_bwd_fused(self, dy, u, g, ss, act, x1, x2, wname, bname, K, need_dx1=True, need_dx2=True, dx1=None,
                         dx2=None, dadd=None, rps=1):

@@ -59,6 +59,15 @@ int dq_conv_bwd_fused(const float* dy, const float* u, const float* g, const flo
                       const float* x1, int c1, const float* x2, int c2, const float* w, const float* dadd,
                       float* dx1, int acc1, float* dx2, int acc2, float* dw, float* db, float* dg, float* dss,
                       int cout, int K, int R, int L, int rows_per_sample, void* stream);
+/* Re-indexing glue that lets the backward of Upsample (nearest x2 + Conv1d k3, unet1d.py:93-96) and Downsample
+ * (Conv1d k4 s2 p1, unet1d.py:110) run through dq_conv_bwd_fused: y[2j] = y[2j+1] = x[j]; dx[j] (+)= d[2j] + d[2j+1];
+ * space-to-depth x (R,C,L) -> (R,2C,L/2) [even samples | odd samples] and back; k4 weights (co,ci,4) <-> k3 weights
+ * (co,2ci,3) (dir 0: pack, dir 1: w4 += unpack(w3)). */
+int dq_upsample2x(const float* x, float* y, long n, void* stream);
+int dq_fold2x(const float* d, float* dx, long n, int acc, void* stream);
+int dq_s2d(const float* x, float* y, int R, int C, int L, void* stream);
+int dq_d2s(const float* d, float* dx, int R, int C, int L, int acc, void* stream);
+int dq_down_w(float* w4, float* w3, int co, int ci, int dir, void* stream);
 /* gradient of ConditionalScaleShift (unet1d.py:677-678): per-sample sum d*c and sum d. */
 int dq_sample_dot(const float* d, const float* c, float* dscale, float* dshift, int out_stride, long n_per_sample,
                   int n_samples, void* stream);

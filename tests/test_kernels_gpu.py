@@ -108,12 +108,13 @@ def test_linear_attention_fwd_bwd(ctx, pre, C, L):
         assert rel_err(net._params[k].grad, v.grad) < TF32_TOL, k
 
 
+@pytest.mark.parametrize("L", [80, 1040, 1250])
 @pytest.mark.parametrize("mode", ["down", "up", "last"])
-def test_resample_convs(ctx, mode):
+def test_resample_convs(ctx, mode, L):
     net, P = ctx["net"], ctx["P"]
     net._ensure_grads()
     net._gflat.zero_()
-    R, L = 7, 80
+    R = 7
     g = torch.Generator().manual_seed(3)
     if mode == "down":
         w, bn, K, s, pad, up = "downs.2.3.weight", "downs.2.3.bias", 4, 2, 1, 1
