@@ -685,11 +685,33 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
           accf = a.acc2;
         }
         if (!dst) continue;   // CTA-uniform
+        // accumulate / identity-skip inputs are fetched BEFORE the FMA loop so that their latency hides behind it
         float acc[4][P];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int i = 0; i < P; ++i) acc[j][i] = 0.f;
+        if (ok && (add || accf)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float* d = dst + (size_t)j * a.L;
+            const float* q = add ? add + (size_t)j * a.L : nullptr;
+            if constexpr (BULK && P == 4) {
+              if (q) { const float4 v = __ldg(reinterpret_cast<const float4*>(q)); acc[j][0] += v.x; acc[j][1] += v.y; acc[j][2] += v.z; acc[j][P - 1] += v.w; }
+              if (accf) { const float4 v = *reinterpret_cast<const float4*>(d); acc[j][0] += v.x; acc[j][1] += v.y; acc[j][2] += v.z; acc[j][P - 1] += v.w; }
+            } else if constexpr (BULK && P == 2) {
+              if (q) { const float2 v = __ldg(reinterpret_cast<const float2*>(q)); acc[j][0] += v.x; acc[j][P - 1] += v.y; }
+              if (accf) { const float2 v = *reinterpret_cast<const float2*>(d); acc[j][0] += v.x; acc[j][P - 1] += v.y; }
+            } else {
+#pragma unroll
+              for (int i = 0; i < P; ++i)
+                if (l + i < a.L) {
+                  if (q) acc[j][i] += __ldg(q + i);
+                  if (accf) acc[j][i] += d[i];
+                }
+            }
+          }
+        }
 #pragma unroll 4
         for (int co = 0; co < COUT; ++co) {
           float dwin[P + 2];   // du[co][pos - 1 .. pos + P]
@@ -712,26 +734,11 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float* d = dst + (size_t)j * a.L;
-            if constexpr (BULK && P == 4) {
-              float4 v = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][P - 1]);
-              if (add) { const float4 q = __ldg(reinterpret_cast<const float4*>(add + (size_t)j * a.L)); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
-              if (accf) { const float4 q = *reinterpret_cast<const float4*>(d); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
-              *reinterpret_cast<float4*>(d) = v;
-            } else if constexpr (BULK && P == 2) {
-              float2 v = make_float2(acc[j][0], acc[j][P - 1]);
-              if (add) { const float2 q = __ldg(reinterpret_cast<const float2*>(add + (size_t)j * a.L)); v.x += q.x; v.y += q.y; }
-              if (accf) { const float2 q = *reinterpret_cast<const float2*>(d); v.x += q.x; v.y += q.y; }
-              *reinterpret_cast<float2*>(d) = v;
-            } else {   // unaligned rows: scalar accesses (positions beyond L are masked individually)
+            if constexpr (BULK && P == 4) *reinterpret_cast<float4*>(d) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][P - 1]);
+            else if constexpr (BULK && P == 2) *reinterpret_cast<float2*>(d) = make_float2(acc[j][0], acc[j][P - 1]);
+            else {
 #pragma unroll
-              for (int i = 0; i < P; ++i) {
-                if (l + i < a.L) {
-                  float v = acc[j][i];
-                  if (add) v += __ldg(add + (size_t)j * a.L + i);
-                  if (accf) v += d[i];
-                  d[i] = v;
-                }
-              }
+              for (int i = 0; i < P; ++i) if (l + i < a.L) d[i] = acc[j][i];
             }
           }
         }
