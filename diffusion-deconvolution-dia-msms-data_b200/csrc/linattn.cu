@@ -125,25 +125,30 @@ __device__ __forceinline__ float quad_sum(float v) {
   return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
-// Thread j normalises position n0 + j (RMSNorm over C with gain g) and writes the TF32-rounded row xn_s[j][0..CP)
-// and column xnT_s[0..CP)[j]; invalid positions give zeros.
+// Software pipeline over the 128-position sub-tiles: the C raw inputs of the NEXT sub-tile are fetched into registers
+// (load_x) before the slab loop of the current one, so their HBM latency hides behind the MMA / softmax work.
 template <int C>
-__device__ __forceinline__ void stage_xn(const float* __restrict__ x, const float* __restrict__ g, int r, int L, int n0,
-                                         int n_end, float* xn_s, float* xnT_s, float* inv_s) {
-  using T = TC<C>;
-  const int j = threadIdx.x, n = n0 + j;
+__device__ __forceinline__ void load_x(const float* __restrict__ x, int r, int L, int n0, int n_end, float (&v)[C]) {
+  const int n = n0 + threadIdx.x;
   const bool ok = n < n_end;
+#pragma unroll
+  for (int c = 0; c < C; ++c) v[c] = ok ? __ldg(x + ((size_t)r * C + c) * L + n) : 0.f;
+}
+// Thread j normalises its position (RMSNorm over C with gain g) and writes the TF32-rounded row xn_s[j][0..CP)
+// and column xnT_s[0..CP)[j]; invalid positions (all-zero inputs) give zeros.
+template <int C>
+__device__ __forceinline__ void stage_xn(const float (&xin)[C], const float* __restrict__ g, float* xn_s, float* xnT_s,
+                                         float* inv_s) {
+  using T = TC<C>;
+  const int j = threadIdx.x;
   float v[T::CP];
   float s2 = 0.f;
 #pragma unroll
-  for (int c = 0; c < T::CP; ++c) {
-    v[c] = (c < C && ok) ? __ldg(x + ((size_t)r * C + (c < C ? c : 0)) * L + n) : 0.f;
-    s2 = fmaf(v[c], v[c], s2);
-  }
+  for (int c = 0; c < C; ++c) s2 = fmaf(xin[c], xin[c], s2);
   const float inv = 1.f / fmaxf(sqrtf(s2), 1e-12f);
   const float sc = inv * sqrtf((float)C);
 #pragma unroll
-  for (int c = 0; c < T::CP; ++c) v[c] = (c < C) ? __uint_as_float(rtf(v[c] * sc * __ldg(g + (c < C ? c : 0)))) : 0.f;
+  for (int c = 0; c < T::CP; ++c) v[c] = (c < C) ? __uint_as_float(rtf(xin[c < C ? c : 0] * sc * __ldg(g + (c < C ? c : 0)))) : 0.f;
   float4* row = reinterpret_cast<float4*>(xn_s + j * T::XS);
 #pragma unroll
   for (int c4 = 0; c4 < T::CP / 4; ++c4) row[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
@@ -334,9 +339,12 @@ __global__ void __launch_bounds__(128) la_stats_kernel(LAArgs a) {
       for (int i = 0; i < 4; ++i) Macc[mt][ct][i] = 0.f;
   }
 
+  float xv[C];
+  load_x<C>(a.x, r, a.L, n_begin, n_end, xv);
   for (int n0 = n_begin; n0 < n_end; n0 += SP) {
-    stage_xn<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, xnT_s, nullptr);
+    stage_xn<C>(xv, a.g_pre, xn_s, xnT_s, nullptr);
     __syncthreads();
+    if (n0 + SP < n_end) load_x<C>(a.x, r, a.L, n0 + SP, n_end, xv);
     const int nfull = min(SP, n_end - n0) / 16, nslab = min(SP / 16, (n_end - n0 + 15) / 16);
     for (int s = 0; s < nfull; ++s) stats_slab<C, true>(xn_s, xnT_s, s, g, t, 16, wk, m_run, nm2, s_run, Macc);
     if (nslab > nfull) stats_slab<C, false>(xn_s, xnT_s, nfull, g, t, n_end - n0 - 16 * nfull, wk, m_run, nm2, s_run, Macc);
@@ -432,9 +440,14 @@ __global__ void __launch_bounds__(128) la_out_kernel(LAArgs a) {
         bg[kd][ct][i] = f2tf(c < C ? a.gmat[((size_t)r * C + c) * kHD + h * 32 + 8 * kd + 2 * t + i] : 0.f);
       }
 
+  float xv[C], xcur[C];
+  load_x<C>(a.x, r, a.L, n_begin, n_end, xv);
   for (int n0 = n_begin; n0 < n_end; n0 += SP) {
-    stage_xn<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, nullptr, nullptr);
+    stage_xn<C>(xv, a.g_pre, xn_s, nullptr, nullptr);
+#pragma unroll
+    for (int c = 0; c < C; ++c) xcur[c] = xv[c];   // residual input of this sub-tile's epilogue
     __syncthreads();
+    if (n0 + SP < n_end) load_x<C>(a.x, r, a.L, n0 + SP, n_end, xv);
     const int nslab = min(SP / 16, (n_end - n0 + 15) / 16);
     for (int s = 0; s < nslab; ++s) {
       uint32_t ax[T::KC][4];
@@ -478,7 +491,7 @@ __global__ void __launch_bounds__(128) la_out_kernel(LAArgs a) {
         for (int c = 0; c < C; ++c) {
           const size_t idx = ((size_t)r * C + c) * a.L + n;
           if (a.ypre) a.ypre[idx] = y[c];
-          a.out[idx] = fmaf(y[c] * sc, a.g_out[c], __ldg(a.x + idx));
+          a.out[idx] = fmaf(y[c] * sc, a.g_out[c], xcur[c]);
         }
       }
     }
@@ -491,7 +504,7 @@ __global__ void __launch_bounds__(128) la_out_kernel(LAArgs a) {
 // Reductions over positions (Gq = Qs^T dY, dWq = dQr^T Xn) read Qs / dQr back from warp-private shared tiles in
 // the transposed role.
 template <int C>
-__global__ void __launch_bounds__(128, (C <= 8 ? 5 : 1)) la_bwd_q_kernel(LAArgs a) {
+__global__ void __launch_bounds__(128, (C <= 4 ? 5 : (C <= 8 ? 4 : 1))) la_bwd_q_kernel(LAArgs a) {
   using T = TC<C>;
   extern __shared__ float4 dyn_smem4[];
   float* xn_s = reinterpret_cast<float*>(dyn_smem4);   // SP * XS
@@ -539,8 +552,12 @@ __global__ void __launch_bounds__(128, (C <= 8 ? 5 : 1)) la_bwd_q_kernel(LAArgs 
   if (threadIdx.x < 2 * C) acc_s[threadIdx.x] = 0.f;
   __syncthreads();
 
+  float xv[C], yv[C], drv[C];
+  load_x<C>(a.x, r, a.L, n_begin, n_end, xv);
+  load_x<C>(a.ypre, r, a.L, n_begin, n_end, yv);
+  load_x<C>(a.dres, r, a.L, n_begin, n_end, drv);
   for (int n0 = n_begin; n0 < n_end; n0 += SP) {
-    stage_xn<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, xnT_s, nullptr);
+    stage_xn<C>(xv, a.g_pre, xn_s, xnT_s, nullptr);
     {  // d y = RMSNorm_out backward of d res, thread j = position
       const int j = threadIdx.x, n = n0 + j;
       const bool ok = n < n_end;
@@ -548,9 +565,8 @@ __global__ void __launch_bounds__(128, (C <= 8 ? 5 : 1)) la_bwd_q_kernel(LAArgs 
       float s2 = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const size_t idx = ((size_t)r * C + c) * a.L + n;
-        y[c] = ok ? __ldg(a.ypre + idx) : 0.f;
-        dr[c] = ok ? __ldg(a.dres + idx) : 0.f;
+        y[c] = yv[c];
+        dr[c] = drv[c];
         s2 = fmaf(y[c], y[c], s2);
       }
       const float nrm = sqrtf(s2), inv = 1.f / fmaxf(nrm, 1e-12f);
@@ -581,6 +597,11 @@ __global__ void __launch_bounds__(128, (C <= 8 ? 5 : 1)) la_bwd_q_kernel(LAArgs 
       for (int c4 = 0; c4 < T::CP / 4; ++c4) row[c4] = make_float4(dv[4 * c4], dv[4 * c4 + 1], dv[4 * c4 + 2], dv[4 * c4 + 3]);
     }
     __syncthreads();
+    if (n0 + SP < n_end) {
+      load_x<C>(a.x, r, a.L, n0 + SP, n_end, xv);
+      load_x<C>(a.ypre, r, a.L, n0 + SP, n_end, yv);
+      load_x<C>(a.dres, r, a.L, n0 + SP, n_end, drv);
+    }
     const int nslab = min(SP / 16, (n_end - n0 + 15) / 16);
     for (int s = 0; s < nslab; ++s) {
       float qs[4][4], dqs[4][4];
@@ -757,7 +778,7 @@ __global__ void __launch_bounds__(128) la_bwd_combine_kernel(LAArgs a, int rows_
 
 // ------------------------------------------------------------------------------------------- backward: k path
 template <int C>
-__global__ void __launch_bounds__(128, (C <= 8 ? 5 : 1)) la_bwd_kv_kernel(LAArgs a) {
+__global__ void __launch_bounds__(128, (C <= 4 ? 5 : (C <= 8 ? 4 : 1))) la_bwd_kv_kernel(LAArgs a) {
   using T = TC<C>;
   extern __shared__ float4 dyn_smem4[];
   float* xn_s = reinterpret_cast<float*>(dyn_smem4);   // SP * XS
@@ -810,9 +831,16 @@ __global__ void __launch_bounds__(128, (C <= 8 ? 5 : 1)) la_bwd_kv_kernel(LAArgs
       for (int i = 0; i < 4; ++i) dwk[mt][ct][i] = 0.f;
   if (threadIdx.x < C) acc_s[threadIdx.x] = 0.f;
 
+  float xv[C], xcur[C], dqv[C], drv[C];
+  load_x<C>(a.x, r, a.L, n_begin, n_end, xv);
   for (int n0 = n_begin; n0 < n_end; n0 += SP) {
-    stage_xn<C>(a.x, a.g_pre, r, a.L, n0, n_end, xn_s, xnT_s, inv_s);
+    stage_xn<C>(xv, a.g_pre, xn_s, xnT_s, inv_s);
+#pragma unroll
+    for (int c = 0; c < C; ++c) xcur[c] = xv[c];
     __syncthreads();
+    load_x<C>(a.dxnq, r, a.L, n0, n_end, dqv);   // epilogue inputs of this sub-tile, in flight during the slab loop
+    load_x<C>(a.dres, r, a.L, n0, n_end, drv);
+    if (n0 + SP < n_end) load_x<C>(a.x, r, a.L, n0 + SP, n_end, xv);
     const int nslab = min(SP / 16, (n_end - n0 + 15) / 16);
     for (int s = 0; s < nslab; ++s) {
       float kk[4][4], dks[4][4];
@@ -879,10 +907,9 @@ __global__ void __launch_bounds__(128, (C <= 8 ? 5 : 1)) la_bwd_kv_kernel(LAArgs
       for (int c = 0; c < C; ++c) {
         const size_t idx = ((size_t)r * C + c) * a.L + n;
         const float dxn = ok ? yp_s[(0 * SP + j) * T::YS + c] + yp_s[(1 * SP + j) * T::YS + c] +
-                                   yp_s[(2 * SP + j) * T::YS + c] + yp_s[(3 * SP + j) * T::YS + c] + __ldg(a.dxnq + idx)
+                                   yp_s[(2 * SP + j) * T::YS + c] + yp_s[(3 * SP + j) * T::YS + c] + dqv[c]
                              : 0.f;
-        const float xv = ok ? __ldg(a.x + idx) : 0.f;
-        uh[c] = xv * inv;
+        uh[c] = xcur[c] * inv;
         const float dgc = warp_sum(dxn * uh[c] * sqrtC);
         if (lane == 0) atomicAdd(acc_s + c, dgc);
         duh[c] = dxn * a.g_pre[c] * sqrtC;
@@ -894,7 +921,7 @@ __global__ void __launch_bounds__(128, (C <= 8 ? 5 : 1)) la_bwd_kv_kernel(LAArgs
         for (int c = 0; c < C; ++c) {
           const size_t idx = ((size_t)r * C + c) * a.L + n;
           const float d = big ? (duh[c] - uh[c] * dot) * inv : duh[c] * inv;
-          a.dx[idx] = __ldg(a.dres + idx) + d;
+          a.dx[idx] = drv[c] + d;
         }
       }
     }
