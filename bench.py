@@ -187,7 +187,7 @@ def main():
     ap.add_argument("--pool", type=int, default=96, help="synthetic pool size (slices)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sampling", action="store_true")
-    ap.add_argument("--sample-windows", type=int, default=8)
+    ap.add_argument("--sample-windows", type=int, default=32)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -267,9 +267,18 @@ def main():
         l0 = N.launches
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+        if e2e:
+            nxt = draw(loader)
+            loader.prefetch(nxt)
         for i in range(n_timed):
             if e2e:
-                x0, m1, other, m2 = loader.make_batch(draw(loader))
+                # public loader path: the distinct raw slices of THIS step's batch are copied host -> device from the
+                # pinned pool inside the timed region (side stream), overlapped with the previous step's kernels
+                pairs = nxt
+                x0, m1, other, m2 = loader.make_batch(pairs)
+                if i + 1 < n_timed:
+                    nxt = draw(loader)
+                    loader.prefetch(nxt)
                 x0, m1c, cond = ddim._mix_to_device(x0, m1, other, (0.5, 0.5))
                 ddim._train_one_batch(x0, cond, m1c)  # returns loss.item(): device -> host read every step
             else:

@@ -123,8 +123,15 @@ class DeviceBatchLoader:
         elif pool == "pinned":
             self.ms2 = ms2_t.pin_memory()
             self.ms1 = ms1_t.pin_memory()
-            self._stage2 = torch.empty((2 * self.batch_size, self.rt, self.mz), dtype=ms2_t.dtype).pin_memory()
-            self._stage1 = torch.empty((2 * self.batch_size, self.rt), dtype=ms1_t.dtype).pin_memory()
+            # two device staging slots (double buffer) filled by per-slice async copies on a side stream: the H2D
+            # traffic of batch i+1 overlaps the training step of batch i.  Only the DISTINCT slices of a batch travel.
+            nslot = min(2 * self.batch_size, n)
+            self._dstage2 = [torch.empty((nslot, self.rt, self.mz), dtype=ms2_t.dtype, device=self.device) for _ in range(2)]
+            self._dstage1 = [torch.empty((nslot, self.rt), dtype=ms1_t.dtype, device=self.device) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._pending = None     # (pairs, slot, event, pidx, bytes)
+            self._slot = 0
+            self._free_ev = [None, None]   # recorded after the multiplex kernel that last read the slot
         else:
             raise ValueError("pool must be 'hbm' or 'pinned'")
         self.h2d_bytes = 0
@@ -135,22 +142,50 @@ class DeviceBatchLoader:
     def draw(self, nb):
         return [self.dataset.draw_pair() for _ in range(nb)]
 
+    def _issue_copies(self, pairs, stream):
+        """Async H2D of the distinct slices of `pairs` into the next staging slot; returns (slot, event, pidx, bytes)."""
+        slot = self._slot
+        self._slot ^= 1
+        uniq = sorted({i for p in pairs for i in p})
+        pos = {i: k for k, i in enumerate(uniq)}
+        pidx_h = torch.tensor([[pos[a], pos[b]] for a, b in pairs], dtype=torch.long).pin_memory()
+        with torch.cuda.stream(stream):
+            if self._free_ev[slot] is not None:
+                stream.wait_event(self._free_ev[slot])
+            d2, d1 = self._dstage2[slot], self._dstage1[slot]
+            for k, i in enumerate(uniq):
+                d2[k].copy_(self.ms2[i], non_blocking=True)
+            d1[: len(uniq)].copy_(self.ms1[uniq].pin_memory(), non_blocking=True)
+            pidx = pidx_h.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        nbytes = len(uniq) * (self.rt * self.mz * d2.element_size() + self.rt * d1.element_size()) + pidx_h.numel() * 8
+        return slot, ev, pidx, nbytes
+
+    def prefetch(self, pairs):
+        """Start the host->device copies of a future batch on the side stream (pool='pinned')."""
+        if self.pool != "pinned":
+            return
+        self._pending = (pairs,) + self._issue_copies(pairs, self._copy_stream)
+
     def make_batch(self, pairs, want_cond=False, weights=(0.5, 0.5)):
         nb = len(pairs)
         dev = self.device
+        slot = None
         if self.pool == "hbm":
             ms2, ms1 = self.ms2, self.ms1
             pidx = torch.tensor(pairs, dtype=torch.long).to(dev, non_blocking=True)
             self.h2d_bytes = pidx.numel() * 8
         else:
-            flat = [i for p in pairs for i in p]
-            idx = torch.tensor(flat, dtype=torch.long)
-            torch.index_select(self.ms2, 0, idx, out=self._stage2[: 2 * nb])
-            torch.index_select(self.ms1, 0, idx, out=self._stage1[: 2 * nb])
-            ms2 = self._stage2[: 2 * nb].to(dev, non_blocking=True)
-            ms1 = self._stage1[: 2 * nb].to(dev, non_blocking=True)
-            pidx = torch.arange(2 * nb, dtype=torch.long).view(nb, 2).to(dev, non_blocking=True)
-            self.h2d_bytes = ms2.numel() * ms2.element_size() + ms1.numel() * ms1.element_size() + pidx.numel() * 8
+            cur = torch.cuda.current_stream(dev)
+            if self._pending is not None and self._pending[0] is pairs:
+                _, slot, ev, pidx, nbytes = self._pending
+            else:
+                slot, ev, pidx, nbytes = self._issue_copies(pairs, self._copy_stream)
+            self._pending = None
+            cur.wait_event(ev)
+            ms2, ms1 = self._dstage2[slot], self._dstage1[slot]
+            self.h2d_bytes = nbytes
         x0 = torch.empty((nb, self.rt, self.mz), dtype=torch.float32, device=dev)
         other = torch.empty_like(x0)
         cond = torch.empty_like(x0) if want_cond else None
@@ -159,10 +194,22 @@ class DeviceBatchLoader:
         stats = torch.empty((nb, 4), dtype=torch.int32, device=dev)
         N.call("dq_multiplex", ms2, ms1, self.dtype_code, pidx, stats, float(weights[0]), float(weights[1]), x0, other,
                cond, m1, m2, nb, self.rt * self.mz, self.rt)
+        if slot is not None:
+            ev2 = torch.cuda.Event()
+            ev2.record(torch.cuda.current_stream(dev))
+            self._free_ev[slot] = ev2
         if want_cond:
             return x0, m1, other, m2, cond
         return x0, m1, other, m2
 
     def __iter__(self):
-        for _ in range(self.batches_per_epoch):
-            yield self.make_batch(self.draw(self.batch_size))
+        nxt = self.draw(self.batch_size)
+        self.prefetch(nxt)
+        for b in range(self.batches_per_epoch):
+            pairs = nxt
+            if b + 1 < self.batches_per_epoch:
+                nxt = self.draw(self.batch_size)
+            batch = self.make_batch(pairs)
+            if b + 1 < self.batches_per_epoch:
+                self.prefetch(nxt)     # copies of the next batch overlap the training step of this one
+            yield batch
