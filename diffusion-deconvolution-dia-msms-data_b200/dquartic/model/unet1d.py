@@ -559,11 +559,11 @@ class UNet1d(nn.Module):
               K, taps, a_row_off, a_k_off, b_k_off, b_tap, nz=1, z_b_koff_step=0, z_c_stride=0, z_b_tap_step=0):
         offs = list(a_row_off) + [0] * (4 - len(a_row_off)) + list(a_k_off) + [0] * (4 - len(a_k_off)) \
             + list(b_k_off) + [0] * (4 - len(b_k_off)) + list(b_tap) + [0] * (4 - len(b_tap))
-        bn = self.gemm_bn if self.gemm_bn else (256 if Nn >= 256 else 128)
+        bn = self.gemm_bn   # 0: the library picks the tile width (multiple of 16) that leaves no ragged last wave
         N.call("dq_gemm_bf16_tn", A, a_rows, a_cols, a_ld, B, b_rows, b_cols, b_ld, b_tap_stride, b_ntaps, C, ldc,
                bias, acc, M, Nn, K, taps, offs, nz, z_b_koff_step, z_b_tap_step, z_c_stride, bn)
 
-    gemm_bn = 0   # 0: 128 x 256 tiles when N >= 256 (measured 1043 vs 889 TFLOP/s at M = 1152), else 128 x 128
+    gemm_bn = 0
 
     def _mid_conv_fwd(self, Ap, wname, bname, b, rt):
         """Ap: bf16 padded [Mp][N] -> fp32 padded [Mp][N] = conv3 over RT (+bias)."""

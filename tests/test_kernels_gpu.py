@@ -160,7 +160,7 @@ def test_tcgen05_gemm_against_torch(ctx, M, Nn, K, taps):
         ref += sh @ Bf[t].T
     ref += bias
     C = torch.empty(M, Nn, device="cuda")
-    for bn in (128, 256):
+    for bn in (128, 256, 208, 0):
         net.gemm_bn = bn
         C.fill_(float("nan"))
         net._gemm(A.cuda(), M, K, K, B.cuda(), Nn, K, K, Nn * K, taps, C, Nn, bias.cuda(), 0, M, Nn, K, taps, offs,

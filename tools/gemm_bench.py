@@ -23,13 +23,13 @@ for mb in (8, 32):
     W = torch.randn(3, Nm, Nm, device=dev).bfloat16()
     U = torch.empty(Mp, Nm, device=dev)
     bias = torch.zeros(Nm, device=dev)
-    for bn in (128, 256):
+    for bn in (128, 256, 208, 0):
         net.gemm_bn = bn
         bench(f"fwd conv mb={mb} bn={bn}", lambda: net._gemm(A, Mp, Nm, Nm, W, Nm, Nm, Nm, Nm * Nm, 3, U, Nm, bias, 0, Mp, Nm, Nm, 3, (-1, 0, 1), (0, 0, 0), (0, 0, 0), (0, 1, 2)), 2.0 * Mp * Nm * Nm * 3)
     ld = (Mp + 7) // 8 * 8
     dUT = torch.randn(Nm, ld, device=dev).bfloat16()
     AT3 = torch.randn(3, Nm, ld, device=dev).bfloat16()
     dW = torch.zeros(3, Nm, Nm, device=dev)
-    for bn in (128, 256):
+    for bn in (128, 256, 208, 0):
         net.gemm_bn = bn
         bench(f"wgrad mb={mb} bn={bn}", lambda: net._gemm(dUT, Nm, Mp, ld, AT3, Nm, Mp, ld, Nm * ld, 3, dW, Nm, None, 1, Nm, Nm, Mp, 1, (0,), (0,), (0,), (0,), nz=3, z_b_tap_step=1, z_c_stride=Nm * Nm), 2.0 * Mp * Nm * Nm * 3)
