@@ -588,7 +588,6 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
       };
       {
         const int idx = 4 + P * tid;
-        const bool ok = tl0 + P * tid < a.L;
         float dyv[P][COUT], uv[P][COUT];
 #pragma unroll
         for (int c = 0; c < COUT; ++c) {
@@ -607,11 +606,15 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
             uv[0][c] = u_t[c * TS + idx];
           }
         }
-        if (!ok) {
+        // positions at or beyond the row end do not exist (with unaligned rows a thread's group can straddle the end)
+        const int nvalid = a.L - (tl0 + P * tid);
+        if (nvalid < P) {
 #pragma unroll
           for (int i = 0; i < P; ++i)
+            if (i >= nvalid) {
 #pragma unroll
-            for (int c = 0; c < COUT; ++c) { dyv[i][c] = 0.f; uv[i][c] = 0.f; }
+              for (int c = 0; c < COUT; ++c) { dyv[i][c] = 0.f; uv[i][c] = 0.f; }
+            }
         }
 #pragma unroll
         for (int i = 0; i < P; ++i) du_at(dyv[i], uv[i], true);
@@ -639,21 +642,22 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
     } else {
       // plain conv: du = dy already sits in the stage; zero the non-existent positions and accumulate the bias gradient
       const int idx = 4 + P * tid;
-      const bool ok = tl0 + P * tid < a.L;
+      const int nvalid = a.L - (tl0 + P * tid);
+      if (nvalid >= P) {
 #pragma unroll
-      for (int c = 0; c < COUT; ++c) {
-        if constexpr (P == 4) {
-          float4 d4 = *reinterpret_cast<const float4*>(du_s + c * TS + idx);
-          if (!ok) { d4 = make_float4(0.f, 0.f, 0.f, 0.f); *reinterpret_cast<float4*>(du_s + c * TS + idx) = d4; }
-          accB[c] += (d4.x + d4.y) + (d4.z + d4.w);
-        } else if constexpr (P == 2) {
-          float2 d2 = *reinterpret_cast<const float2*>(du_s + c * TS + idx);
-          if (!ok) { d2 = make_float2(0.f, 0.f); *reinterpret_cast<float2*>(du_s + c * TS + idx) = d2; }
-          accB[c] += d2.x + d2.y;
-        } else {
-          float d1 = du_s[c * TS + idx];
-          if (!ok) { d1 = 0.f; du_s[c * TS + idx] = 0.f; }
-          accB[c] += d1;
+        for (int c = 0; c < COUT; ++c) {
+          if constexpr (P == 4) { const float4 d4 = *reinterpret_cast<const float4*>(du_s + c * TS + idx); accB[c] += (d4.x + d4.y) + (d4.z + d4.w); }
+          else if constexpr (P == 2) { const float2 d2 = *reinterpret_cast<const float2*>(du_s + c * TS + idx); accB[c] += d2.x + d2.y; }
+          else accB[c] += du_s[c * TS + idx];
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+#pragma unroll
+          for (int i = 0; i < P; ++i) {
+            if (i < nvalid) accB[c] += du_s[c * TS + idx + i];
+            else du_s[c * TS + idx + i] = 0.f;
+          }
         }
       }
       if (H > 0 && tid < COUT) {

@@ -76,6 +76,47 @@ def test_train_step_loss_and_gradients_match_reference_golden():
         assert _cos(delta_got, delta_ref) > 0.99, k
 
 
+@pytest.mark.parametrize("cfg_over,rt,mz", [
+    (dict(dim=8, downsample_dim=320), 5, 320),                                   # BASELINE configs[4] widening: C = 8 .. 32
+    (dict(dim=4, dim_mults=[1, 2, 4], downsample_dim=1300), 3, 1300),            # 3 levels, long rows (multi-tile, L % 4 mixes)
+])
+def test_other_configs_train_step_vs_oracle(cfg_over, rt, mz):
+    """Configurations other than the default: loss and every parameter gradient against the oracle with autograd
+    (widened 2x-channel U-Net of BASELINE.json configs[4]; a shallow net with long, multi-tile rows)."""
+    import dquartic_oracle as O
+    from dquartic.model.model import DDIMDiffusionModel
+
+    cfg = dict(TINY, **cfg_over)
+    net, P = make_net(cfg, seed=5)
+    net.train()
+    d = DDIMDiffusionModel(net, device="cuda")
+    b = 2
+    g = torch.Generator().manual_seed(17)
+    x0 = torch.rand(b, rt, mz, generator=g) * (torch.rand(b, rt, mz, generator=g) < 0.3)
+    c2 = 0.5 * x0 + 0.5 * torch.rand(b, rt, mz, generator=g) * (torch.rand(b, rt, mz, generator=g) < 0.3)
+    c1 = torch.rand(b, rt, generator=g)
+    noise = torch.randn(b, rt, mz, generator=g)
+    t = torch.tensor([40, 870])
+    Pg = {k: v.clone().requires_grad_(not k.endswith("freqs")) for k, v in P.items()}
+    _, _, ab = O.schedule_tables(1000, "cosine")
+    ref_loss, _ = O.train_loss(Pg, cfg, ab, x0, c2, c1, t, noise)
+    ref_loss.backward()
+    net.zero_grad()
+    loss = d.train_step(x0.cuda(), c2.cuda(), c1.cuda(), noise=((noise + 1) * 0.5).cuda(), t=t.cuda())
+    loss.mean().backward()
+    assert abs(float(loss.mean()) - float(ref_loss)) < 2e-3 * float(ref_loss)
+    for k, v in Pg.items():
+        if k.endswith("freqs"):
+            continue
+        # whole-model gradients behind a bf16 mid stage with only b*rt = 6..10 GEMM rows: the worst entry of the
+        # worst tensor wanders between 1 % and 7 % with the input seed for BOTH the pipelined and the plain-load
+        # kernels (tools/cfg_check.py); per-block parity at these shapes is ~1e-6 (test_resnet_block_fwd_bwd)
+        e = rel_err(net._params[k].grad, v.grad)
+        assert e < 1e-1, (k, e)
+        if v.numel() > 64:
+            assert _cos(net._params[k].grad, v.grad) > 0.995, k
+
+
 def test_micro_batched_step_matches_single_pass():
     """Gradient accumulation over micro-batches (with the K-concatenated mid-stage weight-gradient GEMM that runs once
     per optimizer step) must give the same gradients as one pass over the whole batch."""
