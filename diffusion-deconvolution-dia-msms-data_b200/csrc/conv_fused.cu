@@ -465,16 +465,20 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(s ? bar1 : bar0) : "memory");
       return;
     }
-    if (tid < 32) {
+    {
+      // the row copies are spread over ALL warps (row = warp + NW * lane): issued from one warp, the ~rows serialized
+      // UBLKCP iterations made that warp the straggler of the next phase-1 barrier.  Thread 0 posts the expected byte
+      // count; copies of other warps may complete first (the tx-count may go negative, the phase cannot complete
+      // before thread 0's arrive).
       const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
       const int l_lo = max(0, tl0 - 4), l_hi = min(a.L, tl0 + TL + 4);
       const uint32_t bytes = (uint32_t)(l_hi - l_lo) * 4u;
       const uint32_t bar = s ? bar1 : bar0;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const int row = (tid >> 5) + NW * (tid & 31);
+      if (tid == 0 || row < rows) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       if (tid == 0) cf_mbar_expect_tx(bar, bytes * (uint32_t)rows);
-      __syncwarp();
       float* st = stage0 + s * stage_floats;
-      for (int row = tid; row < rows; row += 32) {
+      if (row < rows) {
         const float* src;
         if (row < COUT) src = a.dy + ((size_t)r * COUT + row) * a.L;
         else if (row < DYR) src = a.u + ((size_t)r * COUT + (row - COUT)) * a.L;
@@ -625,19 +629,35 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
           else du_s[c * TS + idx] = dyv[0][c];
         }
       }
-      if (H > 0 && (tid == 0 || tid == NT - 1)) {   // halo positions tl0 - 1 and tl0 + TL (no accumulation)
-        const int idx = tid == 0 ? 3 : TL + 4;
+      if (H > 0 && tid < 32) {
+        // halo positions tl0 - 1 (lanes 0-15) and tl0 + TL (lanes 16-31), one CHANNEL per lane with shuffle reductions:
+        // a serial per-thread evaluation here made warp 0 / 3 the stragglers of the phase-1 barrier (13-18 % of the
+        // kernel in ncu's stall samples)
+        const int side = tid >> 4, c = tid & 15;
+        const int idx = side == 0 ? 3 : TL + 4;
         const int l = tl0 - 4 + idx;
-        const bool ok = l >= 0 && l < a.L;
-        float dyv[COUT], uv[COUT];
+        const bool ok = l >= 0 && l < a.L && c < COUT;
+        const int cc = c < COUT ? c : 0;
+        const float dyv = ok ? du_s[cc * TS + idx] : 0.f;
+        const float uvv = ok ? u_t[cc * TS + idx] : 0.f;
+        float s2 = uvv * uvv;
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) {
-          dyv[c] = ok ? du_s[c * TS + idx] : 0.f;
-          uv[c] = ok ? u_t[c * TS + idx] : 0.f;
-        }
-        du_at(dyv, uv, false);
+        for (int o = 8; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        const bool big = s2 > 1e-24f;
+        const float inv = big ? cf_rsqrt(s2) : 1e12f;
+        const float uh = uvv * inv;
+        // this lane's channel constants straight from memory (indexing the register arrays by lane would spill them)
+        const float sc1 = has_ss ? a.ss[(size_t)sample * a.ss_stride + cc] + 1.f : 1.f;
+        const float gsc = a.g[cc] * sqrtC * sc1;
+        const float shc = has_ss ? a.ss[(size_t)sample * a.ss_stride + COUT + cc] : 0.f;
+        const float z = fmaf(uh, gsc, shc);
+        const float d = dyv * cf_dsilu(z);
+        float dv = d * gsc;
+        float dot = dv * uh;
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) du_s[c * TS + idx] = dyv[c];
+        for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        dv = (dv - uh * (big ? dot : 0.f)) * inv;
+        if (c < COUT) du_s[c * TS + idx] = ok ? dv : 0.f;
       }
     } else {
       // plain conv: du = dy already sits in the stage; zero the non-existent positions and accumulate the bias gradient

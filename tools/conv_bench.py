@@ -19,7 +19,7 @@ def tm(fn, reps=5):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1000
 R = b * rt
-for pre, c1, c2, L in [("downs.0.0", 4, 0, 40000), ("ups.6.0", 4, 4, 40000), ("downs.2.0", 8, 0, 10000), ("ups.0.0", 16, 16, 625)]:
+for pre, c1, c2, L in [("downs.0.0", 4, 0, 40000), ("downs.2.0", 8, 0, 10000), ("ups.4.0", 8, 8, 10000), ("downs.4.0", 12, 0, 2500)]:
     x1 = torch.randn(R, c1, L, device="cuda"); x2 = torch.randn(R, c2, L, device="cuda") if c2 else None
     w, bn, gname = pre + ".block1.proj.weight", pre + ".block1.proj.bias", pre + ".block1.norm.g"
     cout = net.specs[w][0]
