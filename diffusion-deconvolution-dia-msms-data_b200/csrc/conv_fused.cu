@@ -911,8 +911,10 @@ struct ConvFwdTmaArgs {
   const float* res; float* u; float* y;
   int c1, c2, R, L, rows_per_sample, ss_stride, act, tiles_per_row, total_tiles, tiles_per_cta;
 };
+// UP2: the input is the nearest-x2 upsampling of half-length rows (Upsample, unet1d.py:93-96): the half-rate rows are staged
+// and x_up[q] = x_half[q >> 1] is resolved when the taps are read, so the upsampled tensor never exists.
 
-template <int COUT, int K, int P, int NT, bool BULK>
+template <int COUT, int K, int P, int NT, bool BULK, bool UP2>
 __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
   constexpr int TL = NT * P;
   constexpr int TS = TL + 36;
@@ -945,13 +947,14 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
   auto issue = [&](int tile, int s) {
     if (!BULK) {   // any alignment: 4-byte cp.async from every thread, arriving on the same mbarrier
       const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
-      const int l_lo = max(0, tl0 - 4), l_hi = min(a.L, tl0 + TL + 4);
-      const int w = l_hi - l_lo, doff = l_lo - (tl0 - 4);
+      const int Lx = UP2 ? a.L / 2 : a.L, x0 = UP2 ? tl0 / 2 : tl0, xw_ = UP2 ? TL / 2 : TL;   // staged input window
+      const int l_lo = max(0, x0 - 4), l_hi = min(Lx, x0 + xw_ + 4);
+      const int w = l_hi - l_lo, doff = l_lo - (x0 - 4);
       float* st = stage0 + s * stage_floats;
       for (int row = 0; row < rows; ++row) {
         const float* src;
-        if (row < a.c1) src = a.x1 + ((size_t)r * a.c1 + row) * a.L;
-        else if (row < cin) src = a.x2 + ((size_t)r * a.c2 + (row - a.c1)) * a.L;
+        if (row < a.c1) src = a.x1 + ((size_t)r * a.c1 + row) * Lx;
+        else if (row < cin) src = a.x2 + ((size_t)r * a.c2 + (row - a.c1)) * Lx;
         else src = a.res + ((size_t)r * COUT + (row - cin)) * a.L;
         src += l_lo;
         const uint32_t dst = cf_smem_u32(st + row * TS + doff);
@@ -963,7 +966,8 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
     }
     if (tid < 32) {
       const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
-      const int l_lo = max(0, tl0 - 4), l_hi = min(a.L, tl0 + TL + 4);
+      const int Lx = UP2 ? a.L / 2 : a.L, x0 = UP2 ? tl0 / 2 : tl0, xw_ = UP2 ? TL / 2 : TL;
+      const int l_lo = max(0, x0 - 4), l_hi = min(Lx, x0 + xw_ + 4);
       const uint32_t bytes = (uint32_t)(l_hi - l_lo) * 4u;
       const uint32_t bar = s ? bar1 : bar0;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -972,10 +976,10 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
       float* st = stage0 + s * stage_floats;
       for (int row = tid; row < rows; row += 32) {
         const float* src;
-        if (row < a.c1) src = a.x1 + ((size_t)r * a.c1 + row) * a.L;
-        else if (row < cin) src = a.x2 + ((size_t)r * a.c2 + (row - a.c1)) * a.L;
+        if (row < a.c1) src = a.x1 + ((size_t)r * a.c1 + row) * Lx;
+        else if (row < cin) src = a.x2 + ((size_t)r * a.c2 + (row - a.c1)) * Lx;
         else src = a.res + ((size_t)r * COUT + (row - cin)) * a.L;
-        cf_bulk_g2s(cf_smem_u32(st + row * TS + (l_lo - (tl0 - 4))), src + l_lo, bytes, bar);
+        cf_bulk_g2s(cf_smem_u32(st + row * TS + (l_lo - (x0 - 4))), src + l_lo, bytes, bar);
       }
     }
   };
@@ -997,7 +1001,7 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
     if (H > 0) {   // zero padding at the two row ends (positions -1 and L)
       if (tid < cin) {
         if (tl0 == 0) x_t[tid * TS + 3] = 0.f;
-        if (a.L <= tl0 + TL) x_t[tid * TS + (a.L - tl0 + 4)] = 0.f;
+        if (a.L <= tl0 + TL) x_t[tid * TS + (UP2 ? (a.L - tl0) / 2 : a.L - tl0) + 4] = 0.f;
       }
       if (tl0 == 0 || a.L <= tl0 + TL) __syncthreads();   // uniform per tile
     }
@@ -1011,11 +1015,23 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
 #pragma unroll 2
     for (int ci = 0; ci < cin; ++ci) {
       float xw[P + 2];
+      if constexpr (UP2) {
+        // x_up[tl0 + P tid + i - 1] = x_half[(P tid + i - 1) >> 1]  (index -1 >> 1 = -1: the zeroed left neighbour)
+        const float* xh = x_t + ci * TS + 4;
+        if constexpr (P == 4) {
+          const float2 m = *reinterpret_cast<const float2*>(xh + 2 * tid);
+          xw[0] = xh[2 * tid - 1]; xw[1] = m.x; xw[2] = m.x; xw[3] = m.y; xw[P] = m.y; xw[P + 1] = xh[2 * tid + 2];
+        } else {
+#pragma unroll
+          for (int i = 0; i < P + 2; ++i) xw[i] = xh[(P * (int)tid + i - 1) >> 1];
+        }
+      }
       const float* xr = x_t + ci * TS + 4 + P * tid;
-      if constexpr (P == 4) { const float4 m = *reinterpret_cast<const float4*>(xr); xw[1] = m.x; xw[2] = m.y; xw[3] = m.z; xw[P] = m.w; }
+      if constexpr (UP2) {
+      } else if constexpr (P == 4) { const float4 m = *reinterpret_cast<const float4*>(xr); xw[1] = m.x; xw[2] = m.y; xw[3] = m.z; xw[P] = m.w; }
       else if constexpr (P == 2) { const float2 m = *reinterpret_cast<const float2*>(xr); xw[1] = m.x; xw[P] = m.y; }
       else xw[1] = xr[0];
-      if constexpr (K == 3) { xw[0] = xr[-1]; xw[P + 1] = xr[P]; }
+      if constexpr (K == 3 && !UP2) { xw[0] = xr[-1]; xw[P + 1] = xr[P]; }
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const float4* wp = reinterpret_cast<const float4*>(w_s + (ci * K + k) * COUT);
@@ -1086,7 +1102,7 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
   }
 }
 
-template <int COUT, int K, int P, int NT, bool BULK>
+template <int COUT, int K, int P, int NT, bool BULK, bool UP2>
 static int launch_fwd_tma(ConvFwdTmaArgs a, cudaStream_t st) {
   constexpr int TL = NT * P, TS = TL + 36;
   const int cin = a.c1 + a.c2;
@@ -1095,7 +1111,7 @@ static int launch_fwd_tma(ConvFwdTmaArgs a, cudaStream_t st) {
   a.total_tiles = a.tiles_per_row * a.R;
   size_t smem = sizeof(float) * ((size_t)2 * rows * TS + (size_t)cin * K * COUT) + 16;
   if (smem > 220 * 1024) return -6;
-  auto kern = conv_fwd_tma_kernel<COUT, K, P, NT, BULK>;
+  auto kern = conv_fwd_tma_kernel<COUT, K, P, NT, BULK, UP2>;
   static int sm_count = 0;
   if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1110,19 +1126,32 @@ static int launch_fwd_tma(ConvFwdTmaArgs a, cudaStream_t st) {
   return 0;
 }
 
-// Returns 1 if the pipelined kernel took the call, 0 if the shape is not eligible, < 0 on error.
+// Returns 1 if the pipelined kernel took the call, 0 if the shape is not eligible, < 0 on error.  up == 2: x1 has
+// L / 2 columns (nearest-x2 upsampling folded into the tap reads), K == 3, single source, no residual.
 int conv_fwd_tma_try(const float* x1, int c1, const float* x2, int c2, const float* w, const float* bias, int cout, int K,
                      const float* g, const float* ss, int ss_stride, int act, const float* res, float* u, float* y, int R,
-                     int L, int rows_per_sample, cudaStream_t st) {
+                     int L, int rows_per_sample, int up, cudaStream_t st) {
   static int mode = -1;   // DQ_CONV_FWD_NOTMA=1 forces the plain-load kernel (cross-check)
   if (mode < 0) { const char* e = getenv("DQ_CONV_FWD_NOTMA"); mode = (e && e[0] == '1') ? 1 : 0; }
   if (mode == 1 || (K != 1 && K != 3) || L < 128 || c1 + c2 > 64) return 0;
-  const bool al = (L % 4 == 0) && ((((size_t)x1 | (size_t)x2 | (size_t)res | (size_t)u | (size_t)y) & 15) == 0);
+  if (up == 2 && (K != 3 || x2 || res || (L & 1))) return 0;
+  const int Lx = up == 2 ? L / 2 : L;
+  const bool al = (L % 4 == 0) && (Lx % 4 == 0) && ((((size_t)x1 | (size_t)x2 | (size_t)res | (size_t)u | (size_t)y) & 15) == 0);
   ConvFwdTmaArgs a{x1, x2, w, bias, g, ss, res, u, y, c1, c2, R, L, rows_per_sample, ss_stride, act, 0, 0, 0};
   int rc;
 #define DQ_FWD_CASE(CO, KK, PA, PU) \
-  case CO: rc = al ? launch_fwd_tma<CO, KK, PA, 128, true>(a, st) : launch_fwd_tma<CO, KK, PU, 128, false>(a, st); break;
-  if (K == 3) {
+  case CO: rc = al ? launch_fwd_tma<CO, KK, PA, 128, true, false>(a, st) : launch_fwd_tma<CO, KK, PU, 128, false, false>(a, st); break;
+#define DQ_FWD_CASE_UP(CO, PA, PU) \
+  case CO: rc = al ? launch_fwd_tma<CO, 3, PA, 128, true, true>(a, st) : launch_fwd_tma<CO, 3, PU, 128, false, true>(a, st); break;
+  if (up == 2) {
+    switch (cout) {
+      DQ_FWD_CASE_UP(4, 4, 4)
+      DQ_FWD_CASE_UP(8, 4, 2)
+      DQ_FWD_CASE_UP(12, 2, 2)
+      DQ_FWD_CASE_UP(16, 2, 2)
+      default: return 0;
+    }
+  } else if (K == 3) {
     switch (cout) {
       DQ_FWD_CASE(4, 3, 4, 4)
       DQ_FWD_CASE(8, 3, 4, 2)
@@ -1140,6 +1169,7 @@ int conv_fwd_tma_try(const float* x1, int c1, const float* x2, int c2, const flo
     }
   }
 #undef DQ_FWD_CASE
+#undef DQ_FWD_CASE_UP
   return rc == 0 ? 1 : rc;
 }
 
