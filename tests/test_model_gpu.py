@@ -3,6 +3,7 @@
 Tolerances (BASELINE.json north_star): bf16 tensor-core paths rel <= 2e-2, sampled maps cosine >= 0.999,
 loss curve within 1 % over 200 steps."""
 import json
+import os
 import random
 
 import numpy as np
@@ -115,6 +116,54 @@ def test_other_configs_train_step_vs_oracle(cfg_over, rt, mz):
         assert e < 1e-1, (k, e)
         if v.numel() > 64:
             assert _cos(net._params[k].grad, v.grad) > 0.995, k
+
+
+def test_full_size_train_step_vs_oracle():
+    """BASELINE.json's full sizes: the default 1,204,738,391-parameter denoiser on one 34 x 40000 map.  Loss, the
+    whole 1.2 B-element gradient (cosine) and every parameter tensor's gradient against the fp32 CPU oracle."""
+    import dquartic_oracle as O
+    from dquartic.model.model import DDIMDiffusionModel
+
+    cfg = dict(TINY, downsample_dim=40000)
+    rt, mz = 34, 40000
+    net, P = make_net(cfg, seed=2)
+    assert sum(v.numel() for v in P.values()) == 1204738391   # incl. the 8 rotary freqs (SURVEY.md finding 3)
+    net.train()
+    d = DDIMDiffusionModel(net, device="cuda")
+    g = torch.Generator().manual_seed(23)
+    x0 = (torch.rand(1, rt, mz, generator=g) * (torch.rand(1, rt, mz, generator=g) < 0.02)).float()
+    c2 = 0.5 * x0 + 0.5 * torch.rand(1, rt, mz, generator=g) * (torch.rand(1, rt, mz, generator=g) < 0.02)
+    c1 = torch.rand(1, rt, generator=g)
+    noise = torch.randn(1, rt, mz, generator=g)
+    t = torch.tensor([417])
+    net.zero_grad()
+    loss = d.train_step(x0.cuda(), c2.cuda(), c1.cuda(), noise=((noise + 1) * 0.5).cuda(), t=t.cuda())
+    loss.mean().backward()
+    got_loss = float(loss.mean())
+    got = {k: net._params[k].grad.detach().cpu().clone() for k in P if not k.endswith("freqs")}
+    del net, d
+    torch.cuda.empty_cache()
+    torch.set_num_threads(max(1, (os.cpu_count() or 8)))
+    Pg = {k: v.requires_grad_(not k.endswith("freqs")) for k, v in P.items()}
+    _, _, ab = O.schedule_tables(1000, "cosine")
+    ref_loss, _ = O.train_loss(Pg, cfg, ab, x0, c2, c1, t, noise)
+    ref_loss.backward()
+    assert abs(got_loss - float(ref_loss)) < 2e-3 * float(ref_loss), (got_loss, float(ref_loss))
+    num = den_a = den_b = 0.0
+    worst = (0.0, None)
+    for k, gg in got.items():
+        r = Pg[k].grad
+        num += float((gg.double() * r.double()).sum())
+        den_a += float((gg.double() ** 2).sum())
+        den_b += float((r.double() ** 2).sum())
+        c = _cos(gg, r)
+        if gg.numel() > 64 and c < worst[0] + 1 and (worst[1] is None or c < worst[0]):
+            worst = (c, k)
+        if gg.numel() > 64:
+            assert c > 0.99, (k, c)
+    cos_all = num / (den_a ** 0.5 * den_b ** 0.5)
+    print("full size: loss", got_loss, float(ref_loss), "gradient cosine (1.2 B elements)", cos_all, "worst tensor", worst)
+    assert cos_all > 0.999
 
 
 def test_micro_batched_step_matches_single_pass():
