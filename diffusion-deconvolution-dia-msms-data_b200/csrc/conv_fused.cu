@@ -1173,6 +1173,340 @@ int conv_fwd_tma_try(const float* x1, int c1, const float* x2, int c2, const flo
   return rc == 0 ? 1 : rc;
 }
 
+// =====================================================================================================================
+// Fused ResnetBlock forward (unet1d.py:302-323): h1 = Block1(x, scale/shift), out = Block2(h1) + (res_conv(x) | x) in ONE
+// pass.  The h1 tile (with one halo position each side) lives in shared memory, the skip path reads the staged x rows:
+// HBM traffic per position drops from 4 (2 cin + 5 C) B to 4 (cin + [3 C saved for backward] + C) B.
+struct ResFwdArgs {
+  const float* x1; const float* x2;
+  const float* w1; const float* b1; const float* g1; const float* ss;   // block1 (+ per-sample scale/shift)
+  const float* w2; const float* b2; const float* g2;                    // block2
+  const float* wres; const float* bres;                                 // 1x1 skip conv or null (identity: cin == COUT)
+  float* u1; float* h1; float* u2;                                      // optional outputs saved for backward
+  float* out;
+  int c1, c2, R, L, rows_per_sample, ss_stride, tiles_per_row, total_tiles, tiles_per_cta;
+};
+
+template <int COUT, int P, int NT, bool BULK>
+__global__ void __launch_bounds__(NT) resblock_fwd_tma_kernel(ResFwdArgs a) {
+  constexpr int TL = NT * P;
+  constexpr int TS = TL + 36;
+  static_assert(P == 1 || P == 2 || P == 4, "P");
+  static_assert(COUT % 4 == 0 && COUT <= 16, "COUT");
+  extern __shared__ float4 dyn_smem4[];
+  const int cin = a.c1 + a.c2;
+  const bool has_res = a.wres != nullptr;
+  float* stage0 = reinterpret_cast<float*>(dyn_smem4);
+  const int stage_floats = cin * TS;
+  float* h1_s = stage0 + 2 * stage_floats;                // COUT * TS   (position p at index p + 4)
+  float* w1_s = h1_s + COUT * TS;                         // [(ci*3 + k) * COUT + co]
+  float* w2_s = w1_s + cin * 3 * COUT;                    // [(c*3 + k) * COUT + co]
+  float* wr_s = w2_s + COUT * 3 * COUT;                   // [ci * COUT + co]  (has_res)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wr_s + cin * COUT);
+  const int tid = threadIdx.x;
+  const uint32_t bar0 = cf_smem_u32(bars), bar1 = bar0 + 8;
+  if (tid == 0) {
+    cf_mbar_init(bar0, BULK ? 1 : NT);
+    cf_mbar_init(bar1, BULK ? 1 : NT);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < cin * 3 * COUT; i += NT) { const int co = i % COUT, ck = i / COUT; w1_s[i] = a.w1[(size_t)co * cin * 3 + ck]; }
+  for (int i = tid; i < COUT * 3 * COUT; i += NT) { const int co = i % COUT, ck = i / COUT; w2_s[i] = a.w2[(size_t)co * COUT * 3 + ck]; }
+  if (has_res)
+    for (int i = tid; i < cin * COUT; i += NT) { const int co = i % COUT, ci = i / COUT; wr_s[i] = a.wres[(size_t)co * cin + ci]; }
+  __syncthreads();
+  const int t_begin = blockIdx.x * a.tiles_per_cta, t_end = min(a.total_tiles, t_begin + a.tiles_per_cta);
+  const int n_tiles = t_end - t_begin;
+
+  auto issue = [&](int tile, int s) {
+    const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
+    const int l_lo = max(0, tl0 - 4), l_hi = min(a.L, tl0 + TL + 4);
+    float* st = stage0 + s * stage_floats;
+    if (!BULK) {
+      const int w = l_hi - l_lo, doff = l_lo - (tl0 - 4);
+      for (int row = 0; row < cin; ++row) {
+        const float* src = (row < a.c1 ? a.x1 + ((size_t)r * a.c1 + row) * a.L : a.x2 + ((size_t)r * a.c2 + (row - a.c1)) * a.L) + l_lo;
+        const uint32_t dst = cf_smem_u32(st + row * TS + doff);
+        for (int e = tid; e < w; e += NT)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (uint32_t)e), "l"(src + e) : "memory");
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(s ? bar1 : bar0) : "memory");
+      return;
+    }
+    if (tid < 32) {
+      const uint32_t bytes = (uint32_t)(l_hi - l_lo) * 4u;
+      const uint32_t bar = s ? bar1 : bar0;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (tid == 0) cf_mbar_expect_tx(bar, bytes * (uint32_t)cin);
+      __syncwarp();
+      for (int row = tid; row < cin; row += 32) {
+        const float* src = row < a.c1 ? a.x1 + ((size_t)r * a.c1 + row) * a.L : a.x2 + ((size_t)r * a.c2 + (row - a.c1)) * a.L;
+        cf_bulk_g2s(cf_smem_u32(st + row * TS + (l_lo - (tl0 - 4))), src + l_lo, bytes, bar);
+      }
+    }
+  };
+  if (n_tiles > 0) issue(t_begin, 0);
+  if (n_tiles > 1) issue(t_begin + 1, 1);
+
+  const float sqrtC = sqrtf((float)COUT);
+  const bool has_ss = a.ss != nullptr;
+
+  for (int it = 0; it < n_tiles; ++it) {
+    const int tile = t_begin + it, s = it & 1;
+    const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
+    const int sample = r / a.rows_per_sample;
+    float* x_t = stage0 + s * stage_floats;
+    cf_mbar_wait(s ? bar1 : bar0, (uint32_t)((it >> 1) & 1));
+    // conv zero padding at the row ends (positions -1 and L) wherever they fall inside the staged window
+    const bool edge = tl0 == 0 || a.L < tl0 + TL + 4;
+    if (edge) {
+      if (tid < cin) {
+        if (tl0 == 0) x_t[tid * TS + 3] = 0.f;
+        if (a.L < tl0 + TL + 4) x_t[tid * TS + (a.L - tl0 + 4)] = 0.f;
+      }
+      __syncthreads();
+    }
+    const int l = tl0 + P * tid;
+    const int nvalid = a.L - l;                       // positions l + i with i < nvalid exist
+    const size_t base = (size_t)r * COUT * a.L + l;
+
+    // ------------------------------------------------------------ block 1: conv k3 + RMSNorm + scale/shift + SiLU -> h1 tile
+    {
+      float acc[P][COUT];
+#pragma unroll
+      for (int i = 0; i < P; ++i)
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) acc[i][c] = a.b1[c];
+#pragma unroll 2
+      for (int ci = 0; ci < cin; ++ci) {
+        float xw[P + 2];
+        const float* xr = x_t + ci * TS + 4 + P * tid;
+        if constexpr (P == 4) { const float4 m = *reinterpret_cast<const float4*>(xr); xw[1] = m.x; xw[2] = m.y; xw[3] = m.z; xw[P] = m.w; }
+        else if constexpr (P == 2) { const float2 m = *reinterpret_cast<const float2*>(xr); xw[1] = m.x; xw[P] = m.y; }
+        else xw[1] = xr[0];
+        xw[0] = xr[-1]; xw[P + 1] = xr[P];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float4* wp = reinterpret_cast<const float4*>(w1_s + (ci * 3 + k) * COUT);
+#pragma unroll
+          for (int c4 = 0; c4 < COUT / 4; ++c4) {
+            const float4 w4 = wp[c4];
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+              const float xv = xw[i + k];
+              acc[i][4 * c4 + 0] = fmaf(xv, w4.x, acc[i][4 * c4 + 0]);
+              acc[i][4 * c4 + 1] = fmaf(xv, w4.y, acc[i][4 * c4 + 1]);
+              acc[i][4 * c4 + 2] = fmaf(xv, w4.z, acc[i][4 * c4 + 2]);
+              acc[i][4 * c4 + 3] = fmaf(xv, w4.w, acc[i][4 * c4 + 3]);
+            }
+          }
+        }
+      }
+      if (a.u1 && nvalid > 0) {
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          if constexpr (BULK && P == 4) *reinterpret_cast<float4*>(a.u1 + base + (size_t)c * a.L) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[P - 1][c]);
+          else if constexpr (BULK && P == 2) *reinterpret_cast<float2*>(a.u1 + base + (size_t)c * a.L) = make_float2(acc[0][c], acc[P - 1][c]);
+          else {
+#pragma unroll
+            for (int i = 0; i < P; ++i) if (i < nvalid) a.u1[base + (size_t)c * a.L + i] = acc[i][c];
+          }
+        }
+      }
+      float gs[COUT], sh[COUT];
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        const float sc1 = has_ss ? a.ss[(size_t)sample * a.ss_stride + c] + 1.f : 1.f;
+        gs[c] = a.g1[c] * sqrtC * sc1;
+        sh[c] = has_ss ? a.ss[(size_t)sample * a.ss_stride + COUT + c] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        float s2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) s2 = fmaf(acc[i][c], acc[i][c], s2);
+        const float inv = s2 > 1e-24f ? cf_rsqrt(s2) : 1e12f;
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          float z = fmaf(acc[i][c] * inv, gs[c], sh[c]);
+          z = z * cf_rcp(1.f + cf_ex2(-1.4426950408889634f * z));
+          acc[i][c] = (i < nvalid) ? z : 0.f;          // conv2 sees zero padding beyond the row end
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        if constexpr (P == 4) *reinterpret_cast<float4*>(h1_s + c * TS + 4 + P * tid) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[P - 1][c]);
+        else if constexpr (P == 2) *reinterpret_cast<float2*>(h1_s + c * TS + 4 + P * tid) = make_float2(acc[0][c], acc[P - 1][c]);
+        else h1_s[c * TS + 4 + tid] = acc[0][c];
+      }
+      if (a.h1 && nvalid > 0) {
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          if constexpr (BULK && P == 4) *reinterpret_cast<float4*>(a.h1 + base + (size_t)c * a.L) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[P - 1][c]);
+          else if constexpr (BULK && P == 2) *reinterpret_cast<float2*>(a.h1 + base + (size_t)c * a.L) = make_float2(acc[0][c], acc[P - 1][c]);
+          else {
+#pragma unroll
+            for (int i = 0; i < P; ++i) if (i < nvalid) a.h1[base + (size_t)c * a.L + i] = acc[i][c];
+          }
+        }
+      }
+    }
+    if (tid < 32) {
+      // h1 at the two halo positions tl0 - 1 (lanes 0-15) and tl0 + TL (lanes 16-31): one output channel per lane
+      const int side = tid >> 4, c = tid & 15;
+      const int idx = side == 0 ? 3 : TL + 4;
+      const int lp = tl0 - 4 + idx;
+      const bool ok = lp >= 0 && lp < a.L;
+      const int cc = c < COUT ? c : 0;
+      float acc = a.b1[cc];
+      for (int ci = 0; ci < cin; ++ci) {
+        const float* xr = x_t + ci * TS + idx;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc = fmaf(xr[k - 1], w1_s[(ci * 3 + k) * COUT + cc], acc);
+      }
+      if (c >= COUT) acc = 0.f;
+      float s2 = acc * acc;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      const float inv = s2 > 1e-24f ? cf_rsqrt(s2) : 1e12f;
+      const float sc1 = has_ss ? a.ss[(size_t)sample * a.ss_stride + cc] + 1.f : 1.f;
+      const float shc = has_ss ? a.ss[(size_t)sample * a.ss_stride + COUT + cc] : 0.f;
+      float z = fmaf(acc * inv, a.g1[cc] * sqrtC * sc1, shc);
+      z = z * cf_rcp(1.f + cf_ex2(-1.4426950408889634f * z));
+      if (c < COUT) h1_s[c * TS + idx] = ok ? z : 0.f;
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------ block 2: conv k3 + RMSNorm + SiLU, + skip -> out
+    {
+      float acc[P][COUT];
+#pragma unroll
+      for (int i = 0; i < P; ++i)
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) acc[i][c] = a.b2[c];
+#pragma unroll 2
+      for (int ci = 0; ci < COUT; ++ci) {
+        float xw[P + 2];
+        const float* xr = h1_s + ci * TS + 4 + P * tid;
+        if constexpr (P == 4) { const float4 m = *reinterpret_cast<const float4*>(xr); xw[1] = m.x; xw[2] = m.y; xw[3] = m.z; xw[P] = m.w; }
+        else if constexpr (P == 2) { const float2 m = *reinterpret_cast<const float2*>(xr); xw[1] = m.x; xw[P] = m.y; }
+        else xw[1] = xr[0];
+        xw[0] = xr[-1]; xw[P + 1] = xr[P];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float4* wp = reinterpret_cast<const float4*>(w2_s + (ci * 3 + k) * COUT);
+#pragma unroll
+          for (int c4 = 0; c4 < COUT / 4; ++c4) {
+            const float4 w4 = wp[c4];
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+              const float xv = xw[i + k];
+              acc[i][4 * c4 + 0] = fmaf(xv, w4.x, acc[i][4 * c4 + 0]);
+              acc[i][4 * c4 + 1] = fmaf(xv, w4.y, acc[i][4 * c4 + 1]);
+              acc[i][4 * c4 + 2] = fmaf(xv, w4.z, acc[i][4 * c4 + 2]);
+              acc[i][4 * c4 + 3] = fmaf(xv, w4.w, acc[i][4 * c4 + 3]);
+            }
+          }
+        }
+      }
+      if (nvalid > 0) {
+        if (a.u2) {
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) {
+            if constexpr (BULK && P == 4) *reinterpret_cast<float4*>(a.u2 + base + (size_t)c * a.L) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[P - 1][c]);
+            else if constexpr (BULK && P == 2) *reinterpret_cast<float2*>(a.u2 + base + (size_t)c * a.L) = make_float2(acc[0][c], acc[P - 1][c]);
+            else {
+#pragma unroll
+              for (int i = 0; i < P; ++i) if (i < nvalid) a.u2[base + (size_t)c * a.L + i] = acc[i][c];
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+          float s2 = 0.f;
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) s2 = fmaf(acc[i][c], acc[i][c], s2);
+          const float inv = (s2 > 1e-24f ? cf_rsqrt(s2) : 1e12f) * sqrtC;
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) {
+            float z = acc[i][c] * inv * a.g2[c];
+            acc[i][c] = z * cf_rcp(1.f + cf_ex2(-1.4426950408889634f * z));
+          }
+        }
+        // skip path from the staged x rows
+        if (has_res) {
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) {
+            const float bb = a.bres ? a.bres[c] : 0.f;
+#pragma unroll
+            for (int i = 0; i < P; ++i) acc[i][c] += bb;
+          }
+          for (int ci = 0; ci < cin; ++ci) {
+            float xv[P];
+            const float* xr = x_t + ci * TS + 4 + P * tid;
+            if constexpr (P == 4) { const float4 m = *reinterpret_cast<const float4*>(xr); xv[0] = m.x; xv[1] = m.y; xv[2] = m.z; xv[P - 1] = m.w; }
+            else if constexpr (P == 2) { const float2 m = *reinterpret_cast<const float2*>(xr); xv[0] = m.x; xv[P - 1] = m.y; }
+            else xv[0] = xr[0];
+            const float4* wp = reinterpret_cast<const float4*>(wr_s + ci * COUT);
+#pragma unroll
+            for (int c4 = 0; c4 < COUT / 4; ++c4) {
+              const float4 w4 = wp[c4];
+#pragma unroll
+              for (int i = 0; i < P; ++i) {
+                acc[i][4 * c4 + 0] = fmaf(xv[i], w4.x, acc[i][4 * c4 + 0]);
+                acc[i][4 * c4 + 1] = fmaf(xv[i], w4.y, acc[i][4 * c4 + 1]);
+                acc[i][4 * c4 + 2] = fmaf(xv[i], w4.z, acc[i][4 * c4 + 2]);
+                acc[i][4 * c4 + 3] = fmaf(xv[i], w4.w, acc[i][4 * c4 + 3]);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) {
+            const float* xr = x_t + c * TS + 4 + P * tid;
+#pragma unroll
+            for (int i = 0; i < P; ++i) acc[i][c] += xr[i];
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          if constexpr (BULK && P == 4) *reinterpret_cast<float4*>(a.out + base + (size_t)c * a.L) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[P - 1][c]);
+          else if constexpr (BULK && P == 2) *reinterpret_cast<float2*>(a.out + base + (size_t)c * a.L) = make_float2(acc[0][c], acc[P - 1][c]);
+          else {
+#pragma unroll
+            for (int i = 0; i < P; ++i) if (i < nvalid) a.out[base + (size_t)c * a.L + i] = acc[i][c];
+          }
+        }
+      }
+    }
+    __syncthreads();   // everyone is done with stage s and the h1 tile
+    if (it + 2 < n_tiles) issue(tile + 2, s);
+  }
+}
+
+template <int COUT, int P, int NT, bool BULK>
+static int launch_resblock(ResFwdArgs a, cudaStream_t st) {
+  constexpr int TL = NT * P, TS = TL + 36;
+  const int cin = a.c1 + a.c2;
+  a.tiles_per_row = (a.L + TL - 1) / TL;
+  a.total_tiles = a.tiles_per_row * a.R;
+  size_t smem = sizeof(float) * ((size_t)2 * cin * TS + (size_t)COUT * TS + (size_t)cin * 3 * COUT + (size_t)COUT * 3 * COUT + (size_t)cin * COUT) + 32;
+  if (smem > 220 * 1024) return -6;
+  auto kern = resblock_fwd_tma_kernel<COUT, P, NT, BULK>;
+  static int sm_count = 0;
+  if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+  if (occ < 1) return -6;
+  int grid = min(a.total_tiles, sm_count * occ);
+  a.tiles_per_cta = (a.total_tiles + grid - 1) / grid;
+  grid = (a.total_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
+  kern<<<(unsigned)grid, NT, smem, st>>>(a);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace dq
 
 using namespace dq;
@@ -1192,4 +1526,28 @@ DQ_API int dq_conv_bwd_fused(const float* dy, const float* u, const float* g, co
   if (K == 3) return dispatch_fused<3>(a, cout, st);
   if (K == 1) return dispatch_fused<1>(a, cout, st);
   return -2;
+}
+
+// Fused ResnetBlock forward (unet1d.py:302-323).  Returns 0 on success, 1 if the shape is not covered (the caller then
+// composes the block from dq_conv1d_fwd calls), < 0 / cudaError on failure.  u1 / h1 / u2 may be NULL (inference).
+DQ_API int dq_resblock_fwd(const float* x1, int c1, const float* x2, int c2, const float* w1, const float* b1, const float* g1,
+                           const float* ss, int ss_stride, const float* w2, const float* b2, const float* g2,
+                           const float* wres, const float* bres, float* u1, float* h1, float* u2, float* out, int cout,
+                           int R, int L, int rows_per_sample, void* stream) {
+  if (R <= 0 || L <= 0) return 0;
+  const int cin = c1 + c2;
+  if (L < 128 || cin > 32 || (cin & 3) || (c1 & 3) || (!wres && cin != cout)) return 1;
+  static int mode = -1;   // DQ_RESBLOCK_FUSED=0: compose from single-conv kernels (cross-check)
+  if (mode < 0) { const char* e = getenv("DQ_RESBLOCK_FUSED"); mode = (e && e[0] == '0') ? 0 : 1; }
+  if (!mode) return 1;
+  ResFwdArgs a{x1, x2, w1, b1, g1, ss, w2, b2, g2, wres, bres, u1, h1, u2, out, c1, c2, R, L, rows_per_sample, ss_stride, 0, 0, 0};
+  const bool al = (L % 4 == 0) && ((((size_t)x1 | (size_t)x2 | (size_t)u1 | (size_t)h1 | (size_t)u2 | (size_t)out) & 15) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (cout) {
+    case 4: return al ? launch_resblock<4, 4, 128, true>(a, st) : launch_resblock<4, 4, 128, false>(a, st);
+    case 8: return al ? launch_resblock<8, 4, 128, true>(a, st) : launch_resblock<8, 2, 128, false>(a, st);
+    case 12: return al ? launch_resblock<12, 2, 128, true>(a, st) : launch_resblock<12, 1, 128, false>(a, st);
+    case 16: return al ? launch_resblock<16, 2, 128, true>(a, st) : launch_resblock<16, 1, 128, false>(a, st);
+    default: return 1;
+  }
 }

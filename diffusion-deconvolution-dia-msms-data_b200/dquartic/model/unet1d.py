@@ -496,7 +496,24 @@ class UNet1d(nn.Module):
 
     # ---------------------------------------------------------------------------------------------- composite ops
     def _resnet_fwd(self, pre, x1, x2, rps, save):
-        L = x1.shape[2]
+        R, c1, L = x1.shape
+        c2 = x2.shape[1] if x2 is not None else 0
+        cout = self.specs[pre + ".block1.proj.weight"][0]
+        has_res = (pre + ".res_conv.weight") in self.specs
+        # one-pass kernel: Block1 -> Block2 + skip with the h1 tile in shared memory (csrc/conv_fused.cu)
+        out = self._empty(R, cout, L)
+        u1 = self._empty(R, cout, L) if save else None
+        h1 = self._empty(R, cout, L) if save else None
+        u2 = self._empty(R, cout, L) if save else None
+        sso = self.ss_off[pre + ".mlp.1"]
+        rc = N.call("dq_resblock_fwd", x1, c1, x2, c2, self._w(pre + ".block1.proj.weight"),
+                    self._w(pre + ".block1.proj.bias"), self._w(pre + ".block1.norm.g"), _off_ptr(self._SS[:, sso:]),
+                    self.ss_total, self._w(pre + ".block2.proj.weight"), self._w(pre + ".block2.proj.bias"),
+                    self._w(pre + ".block2.norm.g"), self._w(pre + ".res_conv.weight") if has_res else None,
+                    self._w(pre + ".res_conv.bias") if has_res else None, u1, h1, u2, out, cout, R, L, rps, allow=(1,))
+        if rc == 0:
+            return out, (x1, x2, u1, h1, u2)
+        del out, u1, h1, u2
         h1, u1 = self._conv_fwd(x1, x2, pre + ".block1.proj.weight", pre + ".block1.proj.bias", 3, 1, 1, 1, L,
                                 g=pre + ".block1.norm.g", ss=self.ss_off[pre + ".mlp.1"], act=ACT_SILU, save_u=save,
                                 rps=rps)

@@ -45,6 +45,13 @@ int dq_conv1d_fwd(const float* x1, int c1, const float* x2, int c2, const float*
                   const float* w, const float* bias, int cout, int K, int stride, int pad, int up,
                   const float* g, const float* ss, int ss_stride, int act, const float* res,
                   float* u, float* y, int R, int Lin, int Lout, int rows_per_sample, void* stream);
+/* Fused ResnetBlock forward (unet1d.py:302-323): Block1 (conv k3, RMSNorm, per-sample scale/shift, SiLU) -> Block2 (conv k3,
+ * RMSNorm, SiLU) + skip (1x1 res_conv of the concat input, or identity) in one pass; u1 / h1 / u2 (saved for backward)
+ * may be NULL.  Returns 1 (nothing launched) if the shape is not covered: compose from dq_conv1d_fwd instead. */
+int dq_resblock_fwd(const float* x1, int c1, const float* x2, int c2, const float* w1, const float* b1, const float* g1,
+                    const float* ss, int ss_stride, const float* w2, const float* b2, const float* g2, const float* wres,
+                    const float* bres, float* u1, float* h1, float* u2, float* out, int cout, int R, int L,
+                    int rows_per_sample, void* stream);
 /* backward of the RMSNorm / scale-shift / activation epilogue of Block.forward 260-266. */
 int dq_block_bwd(const float* dy, const float* u, const float* g, const float* ss, int ss_stride, int act,
                  float* du, float* dg, float* dss, int C, int R, int L, int rows_per_sample, void* stream);
