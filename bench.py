@@ -5,7 +5,7 @@
 Workload (BASELINE.json configs[1]): default denoiser (1,204,738,391 parameters, dquartic_train_config.json),
 bf16 tensor-core mid stage / fp32 elsewhere, synthetic multiplexed MS2 maps of the config's shape
 (34 x 40000), batch 256 per GPU.  A "step" is one optimizer step over one batch: multiplexing of 256 drawn pairs,
-q_sample, U-Net forward/backward (gradient accumulation over micro-batches), epsilon-MSE, grad-clip 10 + AdamW.
+q_sample, U-Net forward/backward (gradient accumulation over 4 micro-batches of 64), epsilon-MSE, grad-clip 10 + AdamW.
 N > 1 (torchrun): weak scaling, 256 samples per GPU, one bucketed NCCL gradient all-reduce per step.
 
 One JSON line on rank 0:
@@ -183,7 +183,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU per optimizer step")
-    ap.add_argument("--micro-batch", type=int, default=32)
+    ap.add_argument("--micro-batch", type=int, default=64)
     ap.add_argument("--pool", type=int, default=96, help="synthetic pool size (slices)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sampling", action="store_true")
