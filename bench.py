@@ -309,7 +309,7 @@ def main():
 
     extra = {}
     if rank == 0:
-        extra["roofline"] = dominant_kernel_roofline(torch, N, net, dev)
+        extra["roofline"] = dominant_kernel_roofline(torch, N, net, dev, min(B, args.micro_batch))
         extra["step_breakdown"] = {"train_gflop_per_sample": 3 * FWD_GFLOP_PER_SAMPLE,
                                    "achieved_tflops_whole_step": 3 * FWD_GFLOP_PER_SAMPLE * B / ms_step,
                                    "frac_of_bf16_sustained_peak": 3 * FWD_GFLOP_PER_SAMPLE * B / ms_step / peaks()["tensor_sustained"]}
@@ -354,13 +354,12 @@ def _time_ms(torch, fn, reps=3, warm=2):
     return ev0.elapsed_time(ev1) / reps
 
 
-def dominant_kernel_roofline(torch, N, net, dev):
+def dominant_kernel_roofline(torch, N, net, dev, n_samples=64):
     """Live CUDA-event timings (torch's current stream = the launch stream) of the kernel families of the step at the
-    shapes of one micro-batch of 32 samples.  `roofline` = the family with the largest share of the step
+    shapes of one micro-batch (n_samples).  `roofline` = the family with the largest share of the step
     (profiles/): the LinearAttention backward at level 0 (C = 4, L = 40000).  Algorithmic work:
     the reference's four backward bmm's = 2 x 557056 x L FLOP per sample and level."""
     pk = peaks()
-    n_samples = 32
     R, C, L = n_samples * RT, 4, MZ
     net._ensure_grads()
     others = []
@@ -375,7 +374,7 @@ def dominant_kernel_roofline(torch, N, net, dev):
     ach_b = 2.0 * fl_f / (ms_b * 1e-3) / 1e12
     # exp count: 128 (k) + 128 (q) per position forward, recomputed in backward; MUFU.EX2 = 16 / clk / SM
     exp_floor_ms = lambda n_exp: n_exp * R * L / (148 * 16 * 1.965e9) * 1e3
-    main = {"kernel": "dq_linattn_bwd (la_bwd_q + la_bwd_combine + la_bwd_kv), level 0 (C=4, L=40000), 32 samples",
+    main = {"kernel": f"dq_linattn_bwd (la_bwd_q + la_bwd_combine + la_bwd_kv), level 0 (C=4, L=40000), {n_samples} samples",
             "bound": "tensor", "achieved": ach_b, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach_b / pk["tensor"],
             "traffic": None, "ms_per_launch": ms_b, "peak_source": pk["src"],
             "note": "algorithmic FLOPs = the reference's 32x32 per-head bmm's; the kernels factor them through the C "
@@ -383,7 +382,7 @@ def dominant_kernel_roofline(torch, N, net, dev):
                     "MUFU.EX2 + instruction issue, not by the tensor pipe or HBM: MUFU floor "
                     f"{exp_floor_ms(256):.2f} ms vs {ms_b:.2f} ms measured; HBM-algorithmic bytes "
                     f"{8 * C * 4 * R * L / 1e9:.2f} GB = {8 * C * 4 * R * L / 1e9 / (ms_b * 1e-3):.0f} GB/s"}
-    others.append({"kernel": "dq_linattn_fwd (la_stats + la_combine + la_out), level 0, 32 samples", "bound": "tensor",
+    others.append({"kernel": f"dq_linattn_fwd (la_stats + la_combine + la_out), level 0, {n_samples} samples", "bound": "tensor",
                    "achieved": fl_f / (ms_f * 1e-3) / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s",
                    "frac": fl_f / (ms_f * 1e-3) / 1e12 / pk["tensor"], "ms_per_launch": ms_f,
                    "note": f"MUFU floor {exp_floor_ms(256):.2f} ms"})
@@ -417,17 +416,17 @@ def dominant_kernel_roofline(torch, N, net, dev):
     ms = _time_ms(torch, lambda: net._gemm(A, Mp, Nm, Nm, W, Nm, Nm, Nm, Nm * Nm, 3, U, Nm, None, 0, Mp, Nm, Nm, 3,
                                            (-1, 0, 1), (0, 0, 0), (0, 0, 0), (0, 1, 2)), reps=5)
     fl = 2.0 * Mp * Nm * Nm * 3
-    others.append({"kernel": "dq_gemm_bf16_tn (tcgen05 3-tap implicit GEMM, mid Conv1d(10000,10000,3) fwd/dgrad), M=1152",
+    others.append({"kernel": f"dq_gemm_bf16_tn (tcgen05 3-tap implicit GEMM, mid Conv1d(10000,10000,3) fwd/dgrad), M={Mp}",
                    "bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s",
                    "frac": fl / (ms * 1e-3) / 1e12 / pk["tensor"], "ms_per_launch": ms})
-    Kc = 8 * Mp   # weight gradient of one optimizer step: the 8 micro-batches concatenated along K
+    Kc = 256 * (RT + 2)   # weight gradient of one optimizer step: all micro-batches of the 256-sample batch along K
     dUT = torch.randn(Nm, Kc, device=dev).bfloat16()
     AT3 = torch.randn(3, Nm, Kc, device=dev).bfloat16()
     dW = torch.zeros(3, Nm, Nm, device=dev)
     ms = _time_ms(torch, lambda: net._gemm(dUT, Nm, Kc, Kc, AT3, Nm, Kc, Kc, Nm * Kc, 3, dW, Nm, None, 1, Nm, Nm, Kc, 1,
                                            (0,), (0,), (0,), (0,), nz=3, z_b_tap_step=1, z_c_stride=Nm * Nm), reps=2, warm=1)
     fl = 2.0 * Kc * Nm * Nm * 3
-    others.append({"kernel": "dq_gemm_bf16_tn (mid conv wgrad, K = 8 micro-batches x 1152, fp32 accumulate into dW)",
+    others.append({"kernel": f"dq_gemm_bf16_tn (mid conv wgrad, K = {Kc} = 256 samples x 36 padded rows, fp32 accumulate into dW)",
                    "bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s",
                    "frac": fl / (ms * 1e-3) / 1e12 / pk["tensor"], "ms_per_launch": ms})
     del A, W, U, dUT, AT3, dW
