@@ -395,6 +395,15 @@ __device__ __forceinline__ float cf_rsqrt(float x) {
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// acc{0,1} += x * w{0,1} as ONE packed FFMA2 (Blackwell fma.rn.f32x2): halves the issue slots of the FMA-bound loops
+__device__ __forceinline__ void cf_fma2(float& a0, float& a1, float x, float w0, float w1) {
+  unsigned long long acc, xx, ww;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(acc) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w0), "f"(w1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(xx), "l"(ww));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc));
+}
 // d SiLU(z) / dz with single-MUFU exp / reciprocal (|rel err| ~ 1e-6)
 __device__ __forceinline__ float cf_dsilu(float z) {
   const float s = cf_rcp(1.f + cf_ex2(-1.4426950408889634f * z));
@@ -1041,10 +1050,8 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
 #pragma unroll
           for (int i = 0; i < P; ++i) {
             const float xv = xw[i + 1 + k - H];
-            acc[i][4 * c4 + 0] = fmaf(xv, w4.x, acc[i][4 * c4 + 0]);
-            acc[i][4 * c4 + 1] = fmaf(xv, w4.y, acc[i][4 * c4 + 1]);
-            acc[i][4 * c4 + 2] = fmaf(xv, w4.z, acc[i][4 * c4 + 2]);
-            acc[i][4 * c4 + 3] = fmaf(xv, w4.w, acc[i][4 * c4 + 3]);
+            cf_fma2(acc[i][4 * c4 + 0], acc[i][4 * c4 + 1], xv, w4.x, w4.y);
+            cf_fma2(acc[i][4 * c4 + 2], acc[i][4 * c4 + 3], xv, w4.z, w4.w);
           }
         }
       }
@@ -1294,10 +1301,8 @@ __global__ void __launch_bounds__(NT) resblock_fwd_tma_kernel(ResFwdArgs a) {
 #pragma unroll
             for (int i = 0; i < P; ++i) {
               const float xv = xw[i + k];
-              acc[i][4 * c4 + 0] = fmaf(xv, w4.x, acc[i][4 * c4 + 0]);
-              acc[i][4 * c4 + 1] = fmaf(xv, w4.y, acc[i][4 * c4 + 1]);
-              acc[i][4 * c4 + 2] = fmaf(xv, w4.z, acc[i][4 * c4 + 2]);
-              acc[i][4 * c4 + 3] = fmaf(xv, w4.w, acc[i][4 * c4 + 3]);
+              cf_fma2(acc[i][4 * c4 + 0], acc[i][4 * c4 + 1], xv, w4.x, w4.y);
+              cf_fma2(acc[i][4 * c4 + 2], acc[i][4 * c4 + 3], xv, w4.z, w4.w);
             }
           }
         }
@@ -1401,10 +1406,8 @@ __global__ void __launch_bounds__(NT) resblock_fwd_tma_kernel(ResFwdArgs a) {
 #pragma unroll
             for (int i = 0; i < P; ++i) {
               const float xv = xw[i + k];
-              acc[i][4 * c4 + 0] = fmaf(xv, w4.x, acc[i][4 * c4 + 0]);
-              acc[i][4 * c4 + 1] = fmaf(xv, w4.y, acc[i][4 * c4 + 1]);
-              acc[i][4 * c4 + 2] = fmaf(xv, w4.z, acc[i][4 * c4 + 2]);
-              acc[i][4 * c4 + 3] = fmaf(xv, w4.w, acc[i][4 * c4 + 3]);
+              cf_fma2(acc[i][4 * c4 + 0], acc[i][4 * c4 + 1], xv, w4.x, w4.y);
+              cf_fma2(acc[i][4 * c4 + 2], acc[i][4 * c4 + 3], xv, w4.z, w4.w);
             }
           }
         }

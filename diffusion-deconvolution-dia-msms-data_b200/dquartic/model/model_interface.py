@@ -426,6 +426,8 @@ class ModelInterface(object):
         if not (x_0.is_cuda and x_0.dim() == 3):
             return b
         free, _ = torch.cuda.mem_get_info(x_0.device)
+        # blocks cached by torch's allocator are reusable: count them as free
+        free += torch.cuda.memory_reserved(x_0.device) - torch.cuda.memory_allocated(x_0.device)
         per_sample = 1100.0 * x_0.shape[1] * x_0.shape[2]
         return max(1, min(b, 64, int(0.6 * free / per_sample)))
 
