@@ -209,23 +209,54 @@ __device__ __forceinline__ void load_At(const float* scr, int mt, int j, int g, 
   A[0] = p0[0]; A[1] = p0[8]; A[2] = p0[RS]; A[3] = p0[RS + 8];
 }
 // softmax over the 32 columns (4 n8 tiles) of rows g and g+8, times `scale`, in place
+// packed 2 x fp32 arithmetic (Blackwell fma/mul/add.rn.f32x2): one issue slot per two elements.  The element pairs are
+// the adjacent accumulator registers (c0, c1) / (c2, c3) of the MMA fragments, so packing is a register alias.
+__device__ __forceinline__ unsigned long long pk2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// softmax over the 32 columns (4 n8 tiles) of rows g and g+8, times `scale`, in place
 __device__ __forceinline__ void softmax_rows(float (&q)[4][4], float scale) {
+  const unsigned long long l2e = pk2(kLog2e, kLog2e);
 #pragma unroll
   for (int hf = 0; hf < 2; ++hf) {
     float mx = -INFINITY;
 #pragma unroll
     for (int dt = 0; dt < 4; ++dt) mx = fmaxf(mx, fmaxf(q[dt][2 * hf], q[dt][2 * hf + 1]));
     const float nm = -quad_max(mx) * kLog2e;
-    float sm = 0.f;
+    const unsigned long long nm2 = pk2(nm, nm);
+    unsigned long long sm2 = pk2(0.f, 0.f);
 #pragma unroll
     for (int dt = 0; dt < 4; ++dt) {
-      q[dt][2 * hf] = fexp2(fmaf(q[dt][2 * hf], kLog2e, nm));
-      q[dt][2 * hf + 1] = fexp2(fmaf(q[dt][2 * hf + 1], kLog2e, nm));
-      sm += q[dt][2 * hf] + q[dt][2 * hf + 1];
+      float a0, a1;
+      upk2(fma2(pk2(q[dt][2 * hf], q[dt][2 * hf + 1]), l2e, nm2), a0, a1);
+      q[dt][2 * hf] = fexp2(a0);
+      q[dt][2 * hf + 1] = fexp2(a1);
+      sm2 = add2(sm2, pk2(q[dt][2 * hf], q[dt][2 * hf + 1]));
     }
-    const float f = __fdividef(scale, quad_sum(sm));
+    float s0, s1;
+    upk2(sm2, s0, s1);
+    const float f = __fdividef(scale, quad_sum(s0 + s1));
+    const unsigned long long f2 = pk2(f, f);
 #pragma unroll
-    for (int dt = 0; dt < 4; ++dt) { q[dt][2 * hf] *= f; q[dt][2 * hf + 1] *= f; }
+    for (int dt = 0; dt < 4; ++dt) upk2(mul2(pk2(q[dt][2 * hf], q[dt][2 * hf + 1]), f2), q[dt][2 * hf], q[dt][2 * hf + 1]);
   }
 }
 __device__ __forceinline__ void round_tile(const float (&v)[4][4], uint32_t (&o)[4][4]) {
