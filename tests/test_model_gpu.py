@@ -213,6 +213,57 @@ def test_ddim_sampling_matches_reference_golden():
                 assert _cos(pn[i], torch.from_numpy(g[f"pred_noise_{steps}"][i])) >= 0.999, (steps, i)
 
 
+def test_full_size_ddim_sampling_vs_oracle():
+    """DDIM sampling at BASELINE.json's full size (34 x 40000 map, 1.2 B parameters): 3 reverse steps including the
+    x31.6-gain first step (SURVEY.md 3.4 quirk ii) against the fp32 CPU oracle, cosine >= 0.999 (north_star)."""
+    import dquartic_oracle as O
+    from dquartic.model.model import DDIMDiffusionModel
+
+    cfg = dict(TINY, downsample_dim=40000)
+    rt, mz = 34, 40000
+    net, P = make_net(cfg, seed=2)
+    net.eval()
+    d = DDIMDiffusionModel(net, device="cuda")
+    g = torch.Generator().manual_seed(31)
+    x0 = (torch.rand(1, rt, mz, generator=g) * (torch.rand(1, rt, mz, generator=g) < 0.02)).float()
+    c2 = 0.5 * x0 + 0.5 * torch.rand(1, rt, mz, generator=g) * (torch.rand(1, rt, mz, generator=g) < 0.02)
+    c1 = torch.rand(1, rt, generator=g)
+    xT = torch.randn(1, rt, mz, generator=g)
+    with torch.no_grad():
+        x, pn = d.sample(xT.cuda(), c2.cuda(), c1.cuda(), num_steps=3)
+    x, pn = x.cpu(), pn.cpu()
+    del net, d
+    torch.cuda.empty_cache()
+    torch.set_num_threads(max(1, (os.cpu_count() or 8)))
+    _, _, ab = O.schedule_tables(1000, "cosine")
+    with torch.no_grad():
+        xr, pr = O.ddim_sample(P, cfg, ab, xT, c2, c1, 3)
+    cx, cp = _cos(x, xr), _cos(pn, pr)
+    print("full-size DDIM (3 steps): cosine x", cx, "pred_noise", cp)
+    assert cx >= 0.999 and cp >= 0.999
+
+
+def test_pinned_loader_iteration_matches_hbm_pool(tmp_path):
+    """The double-buffered, de-duplicated host->device staging path (pool='pinned', prefetch on a side stream) yields
+    bit-identical batches to the HBM-resident pool for the same draw sequence."""
+    from dquartic.utils.data_loader import DeviceBatchLoader, DIAMSDataset
+    from dquartic.utils.synthetic import synth_pool
+
+    ms2, ms1 = synth_pool(10, 6, 384, seed=5, density=0.3)
+    np.save(tmp_path / "ms2.npy", ms2)
+    np.save(tmp_path / "ms1.npy", ms1)
+    out = {}
+    for pool in ("hbm", "pinned"):
+        ds = DIAMSDataset(ms2_file=str(tmp_path / "ms2.npy"), ms1_file=str(tmp_path / "ms1.npy"), normalize="minmax")
+        random.seed(77)
+        dl = DeviceBatchLoader(ds, 4, "cuda", pool=pool, batches_per_epoch=5)
+        out[pool] = [[t.cpu().clone() for t in batch] for batch in dl]
+        assert len(out[pool]) == 5
+    for ba, bb in zip(out["hbm"], out["pinned"]):
+        for ta, tb in zip(ba, bb):
+            assert torch.equal(ta, tb)
+
+
 def _run_curve(g, lr):
     import dquartic_oracle as O
     from dquartic.model.model import DDIMDiffusionModel
