@@ -67,9 +67,12 @@ struct TC {
   static constexpr int PS = 2 + CP;                                   // partial record: m, s, M[CP]
   static constexpr int YS = C;                                        // row stride of per-head [pos][c] partial tiles (only c < C stored)
 };
+#ifndef LA_OCC4
+#define LA_OCC4 5  // resident CTAs per SM asked of the C = 4 backward kernels
+#endif
 constexpr int SP = 128;  // positions per staged sub-tile (= threads per CTA)
 constexpr int XT = 136;  // row stride of the transposed [c][pos] tiles (= 8 mod 32: 64-bit fragment loads conflict-free)
-constexpr int RS = 36;   // row stride of the warp-private 16 x 32 transpose tiles
+constexpr int RS = 40;   // row stride of the warp-private 16 x 32 transpose tiles (= 8 mod 32, rows permuted: see store_tile16x32)
 constexpr float kLazy = 8.f;  // online-softmax rescale threshold (numerators stay <= e^8)
 
 __device__ __forceinline__ uint32_t f2tf(float x) {  // exact round-to-nearest TF32 (used outside the hot loops)
@@ -134,9 +137,34 @@ __device__ __forceinline__ void load_x(const float* __restrict__ x, int r, int L
 #pragma unroll
   for (int c = 0; c < C; ++c) v[c] = ok ? __ldg(x + ((size_t)r * C + c) * L + n) : 0.f;
 }
+// The same prefetch without registers: 4-byte cp.async into a [C][SP] shared tile (slot [c][thread]); each thread reads
+// back only what it copied itself, so cp.async.wait_group is the only synchronisation.  Used where the register
+// prefetch would be spilled (ptxas stores a just-loaded register to local memory and stalls on the load).
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src, bool ok) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  const int sz = ok ? 4 : 0;   // src-size 0: zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int C>
+__device__ __forceinline__ void prefetch_x(const float* __restrict__ x, int r, int L, int n0, int n_end, float* dst) {
+  const int n = n0 + threadIdx.x;
+  const bool ok = n < n_end;
+  const float* p = x + (size_t)r * C * L + (ok ? n : n_end - 1);
+#pragma unroll
+  for (int c = 0; c < C; ++c) cp_async4(dst + c * SP + threadIdx.x, p + (size_t)c * L, ok);
+}
+template <int C>
+__device__ __forceinline__ void take_x(const float* src, float (&v)[C]) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) v[c] = src[c * SP + threadIdx.x];
+}
 // Thread j normalises its position (RMSNorm over C with gain g) and writes the TF32-rounded row xn_s[j][0..CP)
 // and column xnT_s[0..CP)[j]; invalid positions (all-zero inputs) give zeros.
-template <int C>
+// TROWS = rows of the transposed tile that are written: CP, or C when the caller lets the (never consumed) padding
+// columns of the B operand alias whatever follows the tile in shared memory.
+template <int C, int TROWS = TC<C>::CP>
 __device__ __forceinline__ void stage_xn(const float (&xin)[C], const float* __restrict__ g, float* xn_s, float* xnT_s,
                                          float* inv_s) {
   using T = TC<C>;
@@ -149,12 +177,14 @@ __device__ __forceinline__ void stage_xn(const float (&xin)[C], const float* __r
   const float sc = inv * sqrtf((float)C);
 #pragma unroll
   for (int c = 0; c < T::CP; ++c) v[c] = (c < C) ? __uint_as_float(rtf(xin[c < C ? c : 0] * sc * __ldg(g + (c < C ? c : 0)))) : 0.f;
-  float4* row = reinterpret_cast<float4*>(xn_s + j * T::XS);
+  if (xn_s) {
+    float4* row = reinterpret_cast<float4*>(xn_s + j * T::XS);
 #pragma unroll
-  for (int c4 = 0; c4 < T::CP / 4; ++c4) row[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+    for (int c4 = 0; c4 < T::CP / 4; ++c4) row[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+  }
   if (xnT_s) {
 #pragma unroll
-    for (int c = 0; c < T::CP; ++c) xnT_s[c * XT + j] = v[c];
+    for (int c = 0; c < TROWS; ++c) xnT_s[c * XT + j] = v[c];
   }
   if (inv_s) inv_s[j] = inv;
 }
@@ -195,18 +225,23 @@ __device__ __forceinline__ void load_bT(const float* xT_s, int s, int j, int g, 
     b[ct][1] = __float_as_uint(v.y);
   }
 }
-// store a tile set v[4][4] (rows = positions g / g+8 of the slab, cols = channel 8*tile + 2t, +1)
+// store a tile set v[4][4] (rows = positions g / g+8 of the slab, cols = channel 8*tile + 2t, +1).
+// Position p lives in row p ^ ((p >> 2) & 1): with RS = 8 (mod 32) the 64-bit stores of a half-warp (4 positions x
+// 8 words) and the 32-bit transposed loads of a warp (positions 2t (+1) x 8 channels) both cover all 32 banks once.
 __device__ __forceinline__ void store_tile16x32(float* scr, const uint32_t (&v)[4][4], int g, int t) {
+  float* p = scr + (g ^ (g >> 2)) * RS + 2 * t;
 #pragma unroll
   for (int dt = 0; dt < 4; ++dt) {
-    *reinterpret_cast<uint2*>(scr + g * RS + 8 * dt + 2 * t) = make_uint2(v[dt][0], v[dt][1]);
-    *reinterpret_cast<uint2*>(scr + (g + 8) * RS + 8 * dt + 2 * t) = make_uint2(v[dt][2], v[dt][3]);
+    *reinterpret_cast<uint2*>(p + 8 * dt) = make_uint2(v[dt][0], v[dt][1]);
+    *reinterpret_cast<uint2*>(p + 8 * RS + 8 * dt) = make_uint2(v[dt][2], v[dt][3]);
   }
 }
 // A fragment of the TRANSPOSED tile: rows = channels 16*mt + g (+8), k = positions 8*j + 2t (+1)
 __device__ __forceinline__ void load_At(const float* scr, int mt, int j, int g, int t, uint32_t (&A)[4]) {
-  const uint32_t* p0 = reinterpret_cast<const uint32_t*>(scr) + (8 * j + 2 * t) * RS + 16 * mt + g;
-  A[0] = p0[0]; A[1] = p0[8]; A[2] = p0[RS]; A[3] = p0[RS + 8];
+  const int r0 = (2 * t) ^ (t >> 1);                                  // row of position 2t; position 2t+1 is in row r0 ^ 1
+  const uint32_t* p0 = reinterpret_cast<const uint32_t*>(scr) + (8 * j + r0) * RS + 16 * mt + g;
+  const uint32_t* p1 = p0 + ((t >> 1) ? -RS : RS);
+  A[0] = p0[0]; A[1] = p0[8]; A[2] = p1[0]; A[3] = p1[8];
 }
 // softmax over the 32 columns (4 n8 tiles) of rows g and g+8, times `scale`, in place
 // packed 2 x fp32 arithmetic (Blackwell fma/mul/add.rn.f32x2): one issue slot per two elements.  The element pairs are
@@ -535,16 +570,23 @@ __global__ void __launch_bounds__(128) la_out_kernel(LAArgs a) {
 // Reductions over positions (Gq = Qs^T dY, dWq = dQr^T Xn) read Qs / dQr back from warp-private shared tiles in
 // the transposed role.
 template <int C>
-__global__ void __launch_bounds__(128, (C <= 4 ? 5 : (C <= 8 ? 4 : 1))) la_bwd_q_kernel(LAArgs a) {
+__global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la_bwd_q_kernel(LAArgs a) {
   using T = TC<C>;
   extern __shared__ float4 dyn_smem4[];
+  // C = 4: ONE [pos][8] tile with xn and dy interleaved (xn0, dy0, xn1, dy1, ..): a single A fragment then carries xn
+  // in k = 0..3 and dy in k = 4..7, and the two B operands (Wq^T | 0) and (0 | G) need one register each
+  constexpr bool kMerged = (C == 4);
   float* xn_s = reinterpret_cast<float*>(dyn_smem4);   // SP * XS
-  float* dy_s = xn_s + SP * T::XS;                     // SP * XS
-  float* xnT_s = dy_s + SP * T::XS;                    // CP * XT
-  float* dyT_s = xnT_s + T::CP * XT;                   // CP * XT
-  float* yp_s = dyT_s + T::CP * XT;                    // 4 * SP * YS   per-head d xn_q
+  float* dy_s = xn_s + (kMerged ? 0 : SP * T::XS);     // SP * XS (merged: same tile)
+  // transposed tiles hold only the C real channel rows: rows C..CP-1 of a B fragment (n = channel) alias the next
+  // array; those accumulator columns are never stored
+  float* xnT_s = dy_s + SP * T::XS;                    // C * XT
+  float* dyT_s = xnT_s + C * XT;                       // C * XT
+  float* yp_s = dyT_s + C * XT;                        // 4 * SP * YS   per-head d xn_q
   float* scr = yp_s + 4 * SP * T::YS;                  // 4 warps * 2 tiles * 16 * RS
   float* acc_s = scr + 4 * 2 * 16 * RS;                // 2 * C  (d g_out, d b_out)
+  constexpr bool kAsync = (C == 4);                    // prefetch through shared memory (registers would spill)
+  float* pf_s = acc_s + 2 * C;                         // kAsync: 3 * C * SP (x, ypre, dres of the next sub-tile)
   const int lane = threadIdx.x & 31, h = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int r = blockIdx.y, ch = blockIdx.x;
   const int n_begin = ch * a.chunk, n_end = min(a.L, n_begin + a.chunk);
@@ -561,8 +603,13 @@ __global__ void __launch_bounds__(128, (C <= 4 ? 5 : (C <= 8 ? 4 : 1))) la_bwd_q
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int c = 8 * ks + 2 * t + i, d = h * 32 + 8 * dt + g;
-        bq[dt][ks][i] = f2tf(c < C ? a.wqkv[(size_t)d * C + c] : 0.f);
-        bgA[dt][ks][i] = f2tf(c < C ? a.gmat[((size_t)r * C + c) * kHD + d] : 0.f);   // B[k = c'][n = d] = G[c'][d]
+        if (kMerged) {  // k = t: xn channel t, k = t + 4: dy channel t; only element [0] of each is used
+          bq[dt][ks][i] = f2tf(a.wqkv[(size_t)d * C + t]);
+          bgA[dt][ks][i] = f2tf(a.gmat[((size_t)r * C + t) * kHD + d]);
+        } else {
+          bq[dt][ks][i] = f2tf(c < C ? a.wqkv[(size_t)d * C + c] : 0.f);
+          bgA[dt][ks][i] = f2tf(c < C ? a.gmat[((size_t)r * C + c) * kHD + d] : 0.f);   // B[k = c'][n = d] = G[c'][d]
+        }
       }
 #pragma unroll
   for (int kd = 0; kd < 4; ++kd)
@@ -584,11 +631,24 @@ __global__ void __launch_bounds__(128, (C <= 4 ? 5 : (C <= 8 ? 4 : 1))) la_bwd_q
   __syncthreads();
 
   float xv[C], yv[C], drv[C];
-  load_x<C>(a.x, r, a.L, n_begin, n_end, xv);
-  load_x<C>(a.ypre, r, a.L, n_begin, n_end, yv);
-  load_x<C>(a.dres, r, a.L, n_begin, n_end, drv);
+  if (kAsync) {
+    prefetch_x<C>(a.x, r, a.L, n_begin, n_end, pf_s);
+    prefetch_x<C>(a.ypre, r, a.L, n_begin, n_end, pf_s + C * SP);
+    prefetch_x<C>(a.dres, r, a.L, n_begin, n_end, pf_s + 2 * C * SP);
+    cp_async_commit();
+  } else {
+    load_x<C>(a.x, r, a.L, n_begin, n_end, xv);
+    load_x<C>(a.ypre, r, a.L, n_begin, n_end, yv);
+    load_x<C>(a.dres, r, a.L, n_begin, n_end, drv);
+  }
   for (int n0 = n_begin; n0 < n_end; n0 += SP) {
-    stage_xn<C>(xv, a.g_pre, xn_s, xnT_s, nullptr);
+    if (kAsync) {
+      cp_async_wait0();
+      take_x<C>(pf_s, xv);
+      take_x<C>(pf_s + C * SP, yv);
+      take_x<C>(pf_s + 2 * C * SP, drv);
+    }
+    stage_xn<C, C>(xv, a.g_pre, kMerged ? nullptr : xn_s, xnT_s, nullptr);
     {  // d y = RMSNorm_out backward of d res, thread j = position
       const int j = threadIdx.x, n = n0 + j;
       const bool ok = n < n_end;
@@ -621,17 +681,29 @@ __global__ void __launch_bounds__(128, (C <= 4 ? 5 : (C <= 8 ? 4 : 1))) la_bwd_q
           if (lane == 0) { atomicAdd(acc_s + c, s1); atomicAdd(acc_s + C + c, s2b); }
         }
         dv[c] = __uint_as_float(rtf(d));
-        dyT_s[c * XT + j] = dv[c];
+        if (c < C) dyT_s[c * XT + j] = dv[c];
       }
       float4* row = reinterpret_cast<float4*>(dy_s + j * T::XS);
+      if (kMerged) {  // xn comes back from its own column of the transposed tile (written by this thread)
+        row[0] = make_float4(xnT_s[0 * XT + j], dv[0], xnT_s[1 * XT + j], dv[1]);
+        row[1] = make_float4(xnT_s[2 * XT + j], dv[2], xnT_s[(C > 3 ? 3 : 0) * XT + j], dv[3]);
+      } else {
 #pragma unroll
-      for (int c4 = 0; c4 < T::CP / 4; ++c4) row[c4] = make_float4(dv[4 * c4], dv[4 * c4 + 1], dv[4 * c4 + 2], dv[4 * c4 + 3]);
+        for (int c4 = 0; c4 < T::CP / 4; ++c4) row[c4] = make_float4(dv[4 * c4], dv[4 * c4 + 1], dv[4 * c4 + 2], dv[4 * c4 + 3]);
+      }
     }
     __syncthreads();
     if (n0 + SP < n_end) {
-      load_x<C>(a.x, r, a.L, n0 + SP, n_end, xv);
-      load_x<C>(a.ypre, r, a.L, n0 + SP, n_end, yv);
-      load_x<C>(a.dres, r, a.L, n0 + SP, n_end, drv);
+      if (kAsync) {
+        prefetch_x<C>(a.x, r, a.L, n0 + SP, n_end, pf_s);
+        prefetch_x<C>(a.ypre, r, a.L, n0 + SP, n_end, pf_s + C * SP);
+        prefetch_x<C>(a.dres, r, a.L, n0 + SP, n_end, pf_s + 2 * C * SP);
+        cp_async_commit();
+      } else {
+        load_x<C>(a.x, r, a.L, n0 + SP, n_end, xv);
+        load_x<C>(a.ypre, r, a.L, n0 + SP, n_end, yv);
+        load_x<C>(a.dres, r, a.L, n0 + SP, n_end, drv);
+      }
     }
     const int nslab = min(SP / 16, (n_end - n0 + 15) / 16);
     for (int s = 0; s < nslab; ++s) {
@@ -639,11 +711,19 @@ __global__ void __launch_bounds__(128, (C <= 4 ? 5 : (C <= 8 ? 4 : 1))) la_bwd_q
       {
         uint32_t ax[T::KC][4];
         load_ax<C>(xn_s, s, g, t, ax);
+        if (kMerged) {
 #pragma unroll
-        for (int dt = 0; dt < 4; ++dt) mma_kc<T::KC>(qs[dt], ax, bq[dt]);
-        load_ax<C>(dy_s, s, g, t, ax);
+          for (int dt = 0; dt < 4; ++dt) {
+            mma8_z(qs[dt], ax[0][0], ax[0][1], ax[0][2], ax[0][3], bq[dt][0][0], 0u);
+            mma8_z(dqs[dt], ax[0][0], ax[0][1], ax[0][2], ax[0][3], 0u, bgA[dt][0][0]);
+          }
+        } else {
 #pragma unroll
-        for (int dt = 0; dt < 4; ++dt) mma_kc<T::KC>(dqs[dt], ax, bgA[dt]);
+          for (int dt = 0; dt < 4; ++dt) mma_kc<T::KC>(qs[dt], ax, bq[dt]);
+          load_ax<C>(dy_s, s, g, t, ax);
+#pragma unroll
+          for (int dt = 0; dt < 4; ++dt) mma_kc<T::KC>(dqs[dt], ax, bgA[dt]);
+        }
       }
       // q carries a (1 + 2^-11) factor: the MMA's operand truncation of q (in Gq) and of dQr = q (dQs - ts) (in dWq,
       // d xn_q) is then unbiased without any explicit rounding instruction
@@ -809,15 +889,17 @@ __global__ void __launch_bounds__(128) la_bwd_combine_kernel(LAArgs a, int rows_
 
 // ------------------------------------------------------------------------------------------- backward: k path
 template <int C>
-__global__ void __launch_bounds__(128, (C <= 4 ? 5 : (C <= 8 ? 4 : 1))) la_bwd_kv_kernel(LAArgs a) {
+__global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la_bwd_kv_kernel(LAArgs a) {
   using T = TC<C>;
   extern __shared__ float4 dyn_smem4[];
   float* xn_s = reinterpret_cast<float*>(dyn_smem4);   // SP * XS
-  float* xnT_s = xn_s + SP * T::XS;                    // CP * XT
-  float* yp_s = xnT_s + T::CP * XT;                    // 4 * SP * YS
+  float* xnT_s = xn_s + SP * T::XS;                    // C * XT (see la_bwd_q_kernel)
+  float* yp_s = xnT_s + C * XT;                        // 4 * SP * YS
   float* scr = yp_s + 4 * SP * T::YS;                  // 4 warps * 16 * RS
   float* inv_s = scr + 4 * 16 * RS;                    // SP
   float* acc_s = inv_s + SP;                           // C (d g_pre)
+  constexpr bool kAsync = (C == 4);                    // prefetch through shared memory (see la_bwd_q_kernel)
+  float* pf_s = acc_s + C;                             // kAsync: 4 * C * SP: x (two alternating slots), dxnq, dres
   const int lane = threadIdx.x & 31, h = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int r = blockIdx.y;
   const int n_begin = blockIdx.x * a.chunk, n_end = min(a.L, n_begin + a.chunk);
@@ -863,15 +945,34 @@ __global__ void __launch_bounds__(128, (C <= 4 ? 5 : (C <= 8 ? 4 : 1))) la_bwd_k
   if (threadIdx.x < C) acc_s[threadIdx.x] = 0.f;
 
   float xv[C], xcur[C], dqv[C], drv[C];
-  load_x<C>(a.x, r, a.L, n_begin, n_end, xv);
+  int slot = 0;
+  if (kAsync) {
+    prefetch_x<C>(a.x, r, a.L, n_begin, n_end, pf_s);
+    cp_async_commit();
+  } else {
+    load_x<C>(a.x, r, a.L, n_begin, n_end, xv);
+  }
   for (int n0 = n_begin; n0 < n_end; n0 += SP) {
-    stage_xn<C>(xv, a.g_pre, xn_s, xnT_s, inv_s);
+    if (kAsync) {
+      cp_async_wait0();
+      take_x<C>(pf_s + slot * C * SP, xv);
+    }
+    stage_xn<C, C>(xv, a.g_pre, xn_s, xnT_s, inv_s);
+    if (!kAsync) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) xcur[c] = xv[c];
+      for (int c = 0; c < C; ++c) xcur[c] = xv[c];
+    }
     __syncthreads();
-    load_x<C>(a.dxnq, r, a.L, n0, n_end, dqv);   // epilogue inputs of this sub-tile, in flight during the slab loop
-    load_x<C>(a.dres, r, a.L, n0, n_end, drv);
-    if (n0 + SP < n_end) load_x<C>(a.x, r, a.L, n0 + SP, n_end, xv);
+    if (kAsync) {  // epilogue inputs of this sub-tile and x of the next one, in flight during the slab loop
+      prefetch_x<C>(a.dxnq, r, a.L, n0, n_end, pf_s + 2 * C * SP);
+      prefetch_x<C>(a.dres, r, a.L, n0, n_end, pf_s + 3 * C * SP);
+      if (n0 + SP < n_end) prefetch_x<C>(a.x, r, a.L, n0 + SP, n_end, pf_s + (slot ^ 1) * C * SP);
+      cp_async_commit();
+    } else {
+      load_x<C>(a.dxnq, r, a.L, n0, n_end, dqv);   // epilogue inputs of this sub-tile, in flight during the slab loop
+      load_x<C>(a.dres, r, a.L, n0, n_end, drv);
+      if (n0 + SP < n_end) load_x<C>(a.x, r, a.L, n0 + SP, n_end, xv);
+    }
     const int nslab = min(SP / 16, (n_end - n0 + 15) / 16);
     for (int s = 0; s < nslab; ++s) {
       float kk[4][4], dks[4][4];
@@ -931,6 +1032,13 @@ __global__ void __launch_bounds__(128, (C <= 4 ? 5 : (C <= 8 ? 4 : 1))) la_bwd_k
     {  // thread j = position: RMSNorm_pre backward + residual gradient
       const int j = threadIdx.x, n = n0 + j;
       const bool ok = n < n_end;
+      if (kAsync) {
+        cp_async_wait0();
+        take_x<C>(pf_s + slot * C * SP, xcur);
+        take_x<C>(pf_s + 2 * C * SP, dqv);
+        take_x<C>(pf_s + 3 * C * SP, drv);
+        slot ^= 1;
+      }
       const float inv = inv_s[j];
       float uh[C], duh[C];
       float dot = 0.f;
@@ -991,7 +1099,8 @@ static int la_bwd(const LAArgs& a, cudaStream_t st) {
   using T = TC<C>;
   dim3 grid((unsigned)a.nchunk, (unsigned)a.R);
   {
-    size_t smem = sizeof(float) * (2 * SP * T::XS + 2 * T::CP * XT + 4 * SP * T::YS + 4 * 2 * 16 * RS + 2 * C);
+    size_t smem = sizeof(float) * ((C == 4 ? 1 : 2) * SP * T::XS + 2 * C * XT + 4 * SP * T::YS + 4 * 2 * 16 * RS + 2 * C +
+                                   (C == 4 ? 3 * C * SP : 0));
     cudaFuncSetAttribute(la_bwd_q_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     la_bwd_q_kernel<C><<<grid, 128, smem, st>>>(a);
     DQ_LAUNCH_CHECK();
@@ -1004,7 +1113,7 @@ static int la_bwd(const LAArgs& a, cudaStream_t st) {
     DQ_LAUNCH_CHECK();
   }
   {
-    size_t smem = sizeof(float) * (SP * T::XS + T::CP * XT + 4 * SP * T::YS + 4 * 16 * RS + SP + C);
+    size_t smem = sizeof(float) * (SP * T::XS + C * XT + 4 * SP * T::YS + 4 * 16 * RS + SP + C + (C == 4 ? 4 * C * SP : 0));
     cudaFuncSetAttribute(la_bwd_kv_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     la_bwd_kv_kernel<C><<<grid, 128, smem, st>>>(a);
     DQ_LAUNCH_CHECK();

@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdquartic_b200.so")
+# DQ_B200_LIB: load another build of the same library (kernel A/B experiments, tools/)
+LIB_PATH = os.environ.get("DQ_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libdquartic_b200.so")
 
 # signature mini-language: p = device pointer (torch tensor / None / int), i = int, l = long, f = float,
 # s = stream (filled in automatically), h = host int array (sequence of python ints)
