@@ -36,6 +36,12 @@ struct ConvBwdFusedArgs {
   float* dg;          // (COUT) accumulated or null
   float* dss;         // same layout as ss, accumulated, or null
   int c1, c2, R, L, rows_per_sample, ss_stride, act, acc1, acc2, tiles_per_row, total_tiles, tiles_per_cta;
+  // optional second, 1x1 convolution over the same input (ResnetBlock.res_conv, unet1d.py:299/322): its output gradient
+  // dyo (R, COUT, L), weight wres (COUT, cin); dx gets wres^T dyo added, dwres / dbres are accumulated
+  const float* dyo = nullptr;
+  const float* wres = nullptr;
+  float* dwres = nullptr;
+  float* dbres = nullptr;
 };
 
 // VEC == 4: thread t owns positions 4t .. 4t+3 of the tile (128-bit global accesses; needs L % 4 == 0)
@@ -414,7 +420,7 @@ __device__ __forceinline__ float cf_dsilu(float z) {
 // BULK = true: rows are 16-byte aligned, one cp.async.bulk per row.  BULK = false: any alignment (L % 4 != 0, i.e. the
 // L = 1250 / 625 levels): every thread stages its share of the tile with 4-byte cp.async (LDGSTS) that arrive on the same
 // mbarrier; everything downstream of the staging is identical.
-template <int COUT, int K, int P, int NT, bool EPI, bool BULK>
+template <int COUT, int K, int P, int NT, bool EPI, bool BULK, bool RES = false>
 __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs a) {
   constexpr int TL = NT * P;
   constexpr int TS = TL + 36;
@@ -424,12 +430,14 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
   static_assert(P == 1 || P == 2 || P == 4, "P");
   extern __shared__ float4 dyn_smem4[];
   const int cin = a.c1 + a.c2;                           // multiple of 4 (checked by the launcher), as is c1
-  const int rows = DYR + cin;
+  const int rows = DYR + cin + (RES ? COUT : 0);         // RES: + the res_conv output-gradient rows
   float* stage0 = reinterpret_cast<float*>(dyn_smem4);
   const int stage_floats = rows * TS;
   float* w_s = stage0 + 2 * stage_floats;                // COUT * cin * 4
   float* dw_s = w_s + COUT * cin * 4;                    // COUT * cin * K
-  float* red = dw_s + COUT * cin * K;                    // NW * 2 * COUT
+  float* wres_s = dw_s + COUT * cin * K;                 // RES: COUT * cin
+  float* dwres_s = wres_s + (RES ? COUT * cin : 0);      // RES: COUT * cin
+  float* red = dwres_s + (RES ? COUT * cin : 0);         // NW * 2 * COUT
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + NW * 2 * COUT);
   const int tid = threadIdx.x;
   const uint32_t bar0 = cf_smem_u32(bars), bar1 = bar0 + 8;
@@ -444,6 +452,8 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
     w_s[i] = (k < K) ? a.w[(size_t)pc * K + k] : 0.f;
   }
   for (int i = tid; i < COUT * cin * K; i += NT) dw_s[i] = 0.f;
+  if (RES)
+    for (int i = tid; i < COUT * cin; i += NT) { wres_s[i] = a.wres[i]; dwres_s[i] = 0.f; }
   // stage slots that no copy ever fills (beyond a row end) must hold finite values: 0 * stale stays 0
   for (int i = tid; i < 2 * stage_floats; i += NT) stage0[i] = 0.f;
   __syncthreads();
@@ -462,6 +472,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
         const float* src;
         if (row < COUT) src = a.dy + ((size_t)r * COUT + row) * a.L;
         else if (row < DYR) src = a.u + ((size_t)r * COUT + (row - COUT)) * a.L;
+        else if (RES && row >= DYR + cin) src = a.dyo + ((size_t)r * COUT + (row - DYR - cin)) * a.L;
         else {
           const int ci = row - DYR;
           src = (ci < a.c1) ? a.x1 + ((size_t)r * a.c1 + ci) * a.L : a.x2 + ((size_t)r * a.c2 + (ci - a.c1)) * a.L;
@@ -491,6 +502,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
         const float* src;
         if (row < COUT) src = a.dy + ((size_t)r * COUT + row) * a.L;
         else if (row < DYR) src = a.u + ((size_t)r * COUT + (row - COUT)) * a.L;
+        else if (RES && row >= DYR + cin) src = a.dyo + ((size_t)r * COUT + (row - DYR - cin)) * a.L;
         else {
           const int ci = row - DYR;
           src = (ci < a.c1) ? a.x1 + ((size_t)r * a.c1 + ci) * a.L : a.x2 + ((size_t)r * a.c2 + (ci - a.c1)) * a.L;
@@ -517,6 +529,9 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
   float accS[COUT], accT[COUT], accB[COUT], accG[COUT];
 #pragma unroll
   for (int c = 0; c < COUT; ++c) accS[c] = accT[c] = accB[c] = accG[c] = 0.f;
+  float dwres[RES ? COUT : 1], accR[RES ? COUT : 1];    // RES: dWres[:, ci3] of this thread's segment, sum of dyo
+#pragma unroll
+  for (int c = 0; c < (RES ? COUT : 1); ++c) dwres[c] = accR[c] = 0.f;
   const float sqrtC = sqrtf((float)COUT);
   const bool has_ss = a.ss != nullptr;
   int cur_sample = -1;
@@ -563,6 +578,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
     float* du_s = stage0 + s * stage_floats;                 // dy rows, overwritten in place by du
     const float* u_t = du_s + COUT * TS;                     // [COUT][TS] (EPI only)
     float* x_t = du_s + DYR * TS;                            // [cin][TS]
+    float* yo_t = x_t + cin * TS;                            // RES: [COUT][TS]
     cf_mbar_wait(s ? bar1 : bar0, (uint32_t)((it >> 1) & 1));
 
     // ---------------------------------------------------------------- phase 1: du tile (in place of dy)
@@ -694,6 +710,27 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
         if (a.L <= tl0 + TL) du_s[tid * TS + (a.L - tl0 + 4)] = 0.f;
       }
     }
+    if constexpr (RES) {   // bias gradient of the 1x1 conv; non-existent positions are zeroed for phase 3
+      const int idx = 4 + P * tid;
+      const int nvalid = a.L - (tl0 + P * tid);
+      if (nvalid >= P) {
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+          if constexpr (P == 4) { const float4 d4 = *reinterpret_cast<const float4*>(yo_t + c * TS + idx); accR[c] += (d4.x + d4.y) + (d4.z + d4.w); }
+          else if constexpr (P == 2) { const float2 d2 = *reinterpret_cast<const float2*>(yo_t + c * TS + idx); accR[c] += d2.x + d2.y; }
+          else accR[c] += yo_t[c * TS + idx];
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) {
+#pragma unroll
+          for (int i = 0; i < P; ++i) {
+            if (i < nvalid) accR[c] += yo_t[c * TS + idx + i];
+            else yo_t[c * TS + idx + i] = 0.f;
+          }
+        }
+      }
+    }
     // x rows: exact zeros at the two out-of-range neighbours a valid du can touch (row start / row end)
     if (H > 0 && tid < cin) {
       if (tl0 == 0) x_t[tid * TS + 3] = 0.f;
@@ -763,6 +800,22 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
               for (int k = 0; k < K; ++k) acc[j][i] = fmaf(dwin[i + 1 + H - k], wk[k], acc[j][i]);
           }
         }
+        if constexpr (RES) {   // + wres^T dyo (1x1: no halo)
+#pragma unroll 4
+          for (int co = 0; co < COUT; ++co) {
+            float yo[P];
+            const float* yr = yo_t + co * TS + 4 + P * tid;
+            if constexpr (P == 4) { const float4 m = *reinterpret_cast<const float4*>(yr); yo[0] = m.x; yo[1] = m.y; yo[2] = m.z; yo[P - 1] = m.w; }
+            else if constexpr (P == 2) { const float2 m = *reinterpret_cast<const float2*>(yr); yo[0] = m.x; yo[P - 1] = m.y; }
+            else yo[0] = yr[0];
+            const float4 w4 = *reinterpret_cast<const float4*>(wres_s + co * cin + cb);
+            const float wj[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int i = 0; i < P; ++i) acc[j][i] = fmaf(yo[i], wj[j], acc[j][i]);
+          }
+        }
         if (ok) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -794,6 +847,13 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
 #pragma unroll
             for (int i = 0; i < 4; ++i) dwacc[co][k] = fmaf(dd[i], x6[i + k + 1 - H], dwacc[co][k]);
         }
+        if constexpr (RES) {
+#pragma unroll
+          for (int co = 0; co < COUT; ++co) {
+            const float4 y4 = *reinterpret_cast<const float4*>(yo_t + co * TS + 4 + q);
+            dwres[co] = fmaf(y4.x, xm.x, fmaf(y4.y, xm.y, fmaf(y4.z, xm.z, fmaf(y4.w, xm.w, dwres[co]))));
+          }
+        }
       }
     }
     __syncthreads();   // everyone is done with stage s
@@ -817,18 +877,31 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
     else if (tid < 2 * COUT) { if (a.db) atomicAdd(a.db + tid - COUT, tot); }
   }
   for (int i = tid; i < COUT * cin * K; i += NT) atomicAdd(a.dw + i, dw_s[i]);
+  if constexpr (RES) {
+    if (p3_active) {
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) atomicAdd(dwres_s + co * cin + ci3, dwres[co]);
+    }
+    float v[2 * COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) { v[c] = accR[c]; v[COUT + c] = 0.f; }
+    const float tot = block_sum2c(v);   // its barriers also publish dwres_s
+    if (tid < COUT && a.dbres) atomicAdd(a.dbres + tid, tot);
+    for (int i = tid; i < COUT * cin; i += NT) atomicAdd(a.dwres + i, dwres_s[i]);
+  }
 }
 
-template <int COUT, int K, int P, int NT, bool EPI, bool BULK>
+template <int COUT, int K, int P, int NT, bool EPI, bool BULK, bool RES = false>
 static int launch_fused_tma(ConvBwdFusedArgs a, cudaStream_t st) {
   constexpr int TL = NT * P, TS = TL + 36, NW = NT / 32;
   const int cin = a.c1 + a.c2;
-  const int rows = (EPI ? 2 * COUT : COUT) + cin;
+  const int rows = (EPI ? 2 * COUT : COUT) + cin + (RES ? COUT : 0);
   a.tiles_per_row = (a.L + TL - 1) / TL;
   a.total_tiles = a.tiles_per_row * a.R;
-  size_t smem = sizeof(float) * ((size_t)2 * rows * TS + (size_t)COUT * cin * 4 + (size_t)COUT * cin * K + NW * 2 * COUT) + 16;
+  size_t smem = sizeof(float) * ((size_t)2 * rows * TS + (size_t)COUT * cin * 4 + (size_t)COUT * cin * K +
+                                 (RES ? (size_t)2 * COUT * cin : 0) + NW * 2 * COUT) + 16;
   if (smem > 220 * 1024) return -6;
-  auto kern = conv_bwd_fused_tma_kernel<COUT, K, P, NT, EPI, BULK>;
+  auto kern = conv_bwd_fused_tma_kernel<COUT, K, P, NT, EPI, BULK, RES>;
   static int sm_count = 0;
   if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -878,6 +951,16 @@ static int dispatch_fused(const ConvBwdFusedArgs& a, int cout, cudaStream_t st) 
   if (mode < 0) { const char* e = getenv("DQ_CONV_BWD_NOTMA"); mode = (e && e[0] == '1') ? 1 : 0; }
   // the pipelined kernel covers: plain conv, or RMSNorm (+ scale/shift) + SiLU epilogue; channel counts in fours
   const bool epi_ok = !a.u || (a.g && a.act == 1);
+  if (a.dyo) {   // conv3 + epilogue with the 1x1 res_conv over the same input: pipelined kernel only, COUT 4 / 8
+    if constexpr (K == 3) {
+      const bool al2 = al && (((size_t)a.dyo & 15) == 0);
+      if (mode == 0 && al2 && a.L >= 128 && a.u && a.g && a.act == 1 && (a.c1 & 3) == 0 && (a.c2 & 3) == 0 && !a.dadd) {
+        if (cout == 4) return launch_fused_tma<4, 3, 4, 128, true, true, true>(a, st);
+        if (cout == 8) return launch_fused_tma<8, 3, 2, 128, true, true, true>(a, st);
+      }
+    }
+    return 1;    // not covered: the caller runs the two convolutions separately
+  }
   if (mode == 0 && a.L >= 128 && epi_ok && (a.c1 & 3) == 0 && (a.c2 & 3) == 0) {
     if (al) {
       switch (cout) {
@@ -1529,6 +1612,21 @@ DQ_API int dq_conv_bwd_fused(const float* dy, const float* u, const float* g, co
   if (K == 3) return dispatch_fused<3>(a, cout, st);
   if (K == 1) return dispatch_fused<1>(a, cout, st);
   return -2;
+}
+
+// dq_conv_bwd_fused (K = 3, with epilogue) plus the backward of ResnetBlock.res_conv, a 1x1 convolution over the same
+// input (x1 | x2) whose output gradient is dyo: dx1 / dx2 = conv3^T du + wres^T dyo in ONE pass over x (the separate
+// calls read x twice and read-modify-write dx).  dwres / dbres accumulated.  Returns 1 if the shape is not covered.
+DQ_API int dq_conv_bwd_fused_res(const float* dy, const float* u, const float* g, const float* ss, int ss_stride, int act,
+                                 const float* x1, int c1, const float* x2, int c2, const float* w, float* dx1, float* dx2,
+                                 float* dw, float* db, float* dg, float* dss, const float* dyo, const float* wres,
+                                 float* dwres, float* dbres, int cout, int R, int L, int rows_per_sample, void* stream) {
+  ConvBwdFusedArgs a{dy, u, g, ss, x1, x2, w, nullptr, dx1, dx2, dw, db, dg, dss, c1, c2, R, L, rows_per_sample, ss_stride,
+                     act, 0, 0, 0, 0, 0};
+  a.dyo = dyo; a.wres = wres; a.dwres = dwres; a.dbres = dbres;
+  if (R <= 0 || L <= 0) return 0;
+  if (!dyo || !wres || !dwres || !dx1 || c1 + c2 > 64) return 1;
+  return dispatch_fused<3>(a, cout, (cudaStream_t)stream);
 }
 
 // Fused ResnetBlock forward (unet1d.py:302-323).  Returns 0 on success, 1 if the shape is not covered (the caller then

@@ -530,6 +530,21 @@ class UNet1d(nn.Module):
         dh1, _ = self._conv_bwd_fused(dout, u2, pre + ".block2.norm.g", None, ACT_SILU, h1, None,
                                       pre + ".block2.proj.weight", pre + ".block2.proj.bias", 3, rps=rps)
         has_res = (pre + ".res_conv.weight") in self.specs
+        if has_res and need_dx:
+            # Block1 backward and the res_conv (1x1 over the same input) backward in one pass over x
+            R, c1, L = x1.shape
+            c2 = x2.shape[1] if x2 is not None else 0
+            dx1 = self._empty(R, c1, L)
+            dx2 = self._empty(R, c2, L) if c2 else None
+            ss = self.ss_off[pre + ".mlp.1"]
+            rc = N.call("dq_conv_bwd_fused_res", dh1, u1, self._w(pre + ".block1.norm.g"), _off_ptr(self._SS[:, ss:]),
+                        self.ss_total, ACT_SILU, x1, c1, x2, c2, self._w(pre + ".block1.proj.weight"), dx1, dx2,
+                        self._gw(pre + ".block1.proj.weight"), self._gw(pre + ".block1.proj.bias"),
+                        self._gw(pre + ".block1.norm.g"), _off_ptr(self._dSS[:, ss:]), dout,
+                        self._w(pre + ".res_conv.weight"), self._gw(pre + ".res_conv.weight"),
+                        self._gw(pre + ".res_conv.bias"), dh1.shape[1], R, L, rps, allow=(1,))
+            if rc == 0:
+                return dx1, dx2
         dx1, dx2 = self._conv_bwd_fused(dh1, u1, pre + ".block1.norm.g", self.ss_off[pre + ".mlp.1"], ACT_SILU, x1, x2,
                                         pre + ".block1.proj.weight", pre + ".block1.proj.bias", 3, need_dx1=need_dx,
                                         need_dx2=need_dx, dadd=None if (has_res or not need_dx) else dout, rps=rps)

@@ -66,6 +66,14 @@ int dq_conv_bwd_fused(const float* dy, const float* u, const float* g, const flo
                       const float* x1, int c1, const float* x2, int c2, const float* w, const float* dadd,
                       float* dx1, int acc1, float* dx2, int acc2, float* dw, float* db, float* dg, float* dss,
                       int cout, int K, int R, int L, int rows_per_sample, void* stream);
+/* The backward of ResnetBlock.block1 (conv k3 + epilogue) AND of ResnetBlock.res_conv (1x1 conv over the same concat
+ * input, unet1d.py:299, 322) in one pass: dx1/dx2 = conv3^T du + wres^T dyo, dW, db, dg, d scale/shift, dWres, dbres.
+ * dyo = gradient of the block output (R, cout, L); wres (cout, c1+c2).  Returns 1 (nothing launched) if the shape is
+ * not covered: run dq_conv_bwd_fused twice (K = 3, then K = 1 with acc) instead. */
+int dq_conv_bwd_fused_res(const float* dy, const float* u, const float* g, const float* ss, int ss_stride, int act,
+                          const float* x1, int c1, const float* x2, int c2, const float* w, float* dx1, float* dx2,
+                          float* dw, float* db, float* dg, float* dss, const float* dyo, const float* wres,
+                          float* dwres, float* dbres, int cout, int R, int L, int rows_per_sample, void* stream);
 /* Re-indexing glue that lets the backward of Upsample (nearest x2 + Conv1d k3, unet1d.py:93-96) and Downsample
  * (Conv1d k4 s2 p1, unet1d.py:110) run through dq_conv_bwd_fused: y[2j] = y[2j+1] = x[j]; dx[j] (+)= d[2j] + d[2j+1];
  * space-to-depth x (R,C,L) -> (R,2C,L/2) [even samples | odd samples] and back; k4 weights (co,ci,4) <-> k3 weights

@@ -50,7 +50,8 @@ def test_time_path_and_scale_shift(ctx):
 @pytest.mark.parametrize("pre,c1,c2,L", [("downs.0.0", 4, 0, 320), ("downs.3.1", 8, 0, 40), ("ups.0.0", 16, 16, 5),
                                          ("ups.3.1", 12, 8, 40), ("final_res_block", 4, 4, 320), ("ups.5.0", 8, 4, 160),
                                          ("downs.0.0", 4, 0, 1300), ("ups.6.1", 4, 4, 1030), ("downs.2.0", 8, 0, 2052),
-                                         ("ups.1.0", 16, 12, 515)])
+                                         ("ups.1.0", 16, 12, 515), ("ups.6.0", 4, 4, 2052), ("ups.4.0", 8, 8, 1300),
+                                         ("ups.5.1", 8, 4, 1028)])
 def test_resnet_block_fwd_bwd(ctx, pre, c1, c2, L):
     net, O, P = ctx["net"], ctx["O"], ctx["P"]
     b, rt = 2, 5
