@@ -401,6 +401,23 @@ __device__ __forceinline__ float cf_rsqrt(float x) {
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// TF32 helpers of the tensor-core variant of the backward kernel
+__device__ __forceinline__ uint32_t cf_rtf(float x) { return __float_as_uint(x) + 0x1000u; }   // RN-even-ish: + half ulp, HW truncates
+__device__ __forceinline__ uint32_t cf_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void cf_mma8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cf_mma8_z(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
 // acc{0,1} += x * w{0,1} as ONE packed FFMA2 (Blackwell fma.rn.f32x2): halves the issue slots of the FMA-bound loops
 __device__ __forceinline__ void cf_fma2(float& a0, float& a1, float x, float w0, float w1) {
   unsigned long long acc, xx, ww;
@@ -420,8 +437,17 @@ __device__ __forceinline__ float cf_dsilu(float z) {
 // BULK = true: rows are 16-byte aligned, one cp.async.bulk per row.  BULK = false: any alignment (L % 4 != 0, i.e. the
 // L = 1250 / 625 levels): every thread stages its share of the tile with 4-byte cp.async (LDGSTS) that arrive on the same
 // mbarrier; everything downstream of the staging is identical.
-template <int COUT, int K, int P, int NT, bool EPI, bool BULK, bool RES = false>
+// NCI > 0: phases 2 and 3 run on the tensor cores (mma.sync m16n8k8 TF32, fp32 accumulate) with NCI n8-tiles over the
+// input channels; du is stored TF32-rounded by phase 1, x / dyo fragments are rounded when loaded, weights once.
+// Used for COUT >= 8, where the FFMA form of the two contractions (2 * 3 * COUT * cin FMAs per position) is what bounds
+// the kernel.  Fragment k-slots are permuted (slot t <-> channel 2t, slot t+4 <-> channel 2t+1) so that with the row
+// stride TS = 4 (mod 32) every fragment load covers the 32 banks once.
+template <int COUT, int K, int P, int NT, bool EPI, bool BULK, bool RES = false, int NCI = 0>
 __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs a) {
+  constexpr bool MMA = NCI > 0;
+  static_assert(!MMA || (EPI && K == 3 && COUT % 8 == 0), "MMA variant: conv3 with epilogue, COUT in eights");
+  constexpr int KCO = COUT / 8 > 0 ? COUT / 8 : 1;       // k8 / n8 tiles over the output channels
+  constexpr int MCI = (NCI + 1) / 2 > 0 ? (NCI + 1) / 2 : 1;   // m16 tiles over the input channels (phase 3)
   constexpr int TL = NT * P;
   constexpr int TS = TL + 36;
   constexpr int H = (K - 1) / 2;
@@ -520,11 +546,38 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
   const bool p3_active = tid < nseg * cin;
   const int SL = ((TL + nseg - 1) / nseg + 3) & ~3;
   const int q_begin = seg * SL, q_end = min(TL, q_begin + SL);
-  float dwacc[COUT][K];
+  float dwacc[MMA ? 1 : COUT][K];
 #pragma unroll
-  for (int co = 0; co < COUT; ++co)
+  for (int co = 0; co < (MMA ? 1 : COUT); ++co)
 #pragma unroll
     for (int k = 0; k < K; ++k) dwacc[co][k] = 0.f;
+  // MMA variant: weight fragments (B operand of phase 2) and the dW accumulators (phase 3), per warp
+  const int lane_ = tid & 31, warp_ = tid >> 5, fg = lane_ >> 2, ft = lane_ & 3;
+  uint32_t wB[MMA ? K : 1][KCO][MMA ? NCI : 1][2], wR[KCO][MMA && RES ? NCI : 1][2];
+  float dWf[MMA ? K : 1][MCI][KCO][4], dRf[MCI][KCO][4];
+  if constexpr (MMA) {
+#pragma unroll
+    for (int kc = 0; kc < KCO; ++kc)
+#pragma unroll
+      for (int nt = 0; nt < NCI; ++nt)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int co = 8 * kc + 2 * ft + i, ci = 8 * nt + fg;
+#pragma unroll
+          for (int kk = 0; kk < K; ++kk) wB[kk][kc][nt][i] = cf_tf32(ci < cin ? a.w[((size_t)co * cin + ci) * K + kk] : 0.f);
+          if constexpr (RES) wR[kc][nt][i] = cf_tf32(ci < cin ? a.wres[(size_t)co * cin + ci] : 0.f);
+        }
+#pragma unroll
+    for (int mt = 0; mt < MCI; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < KCO; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int kk = 0; kk < K; ++kk) dWf[kk][mt][nt][i] = 0.f;
+          dRf[mt][nt][i] = 0.f;
+        }
+  }
   // per-thread partial sums: S = sum d*uhat, T = sum d (current sample), B = sum du (bias), G = d g / sqrt(C)
   float accS[COUT], accT[COUT], accB[COUT], accG[COUT];
 #pragma unroll
@@ -647,6 +700,12 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
         }
 #pragma unroll
         for (int i = 0; i < P; ++i) du_at(dyv[i], uv[i], true);
+        if constexpr (MMA) {   // operands of the TF32 contractions: round to nearest once, here
+#pragma unroll
+          for (int i = 0; i < P; ++i)
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) dyv[i][c] = __uint_as_float(cf_rtf(dyv[i][c]));
+        }
 #pragma unroll
         for (int c = 0; c < COUT; ++c) {
           if constexpr (P == 4) *reinterpret_cast<float4*>(du_s + c * TS + idx) = make_float4(dyv[0][c], dyv[1][c], dyv[2][c], dyv[3][c]);
@@ -682,6 +741,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
         dv = (dv - uh * (big ? dot : 0.f)) * inv;
+        if (MMA) dv = __uint_as_float(cf_rtf(dv));
         if (c < COUT) du_s[c * TS + idx] = ok ? dv : 0.f;
       }
     } else {
@@ -739,6 +799,68 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
     __syncthreads();
 
     // ---------------------------------------------------------------- phase 2: dx for the thread's positions
+    if constexpr (MMA) {
+      if (a.dx1 || a.dx2) {
+        // warp w: slabs of 16 positions w, w + NW, ..; D[pos][ci] = sum_k A_k[pos][co] W_k[co][ci] (+ dyo wres)
+        for (int sl = warp_; sl < TL / 16; sl += NW) {
+          const int p0 = 16 * sl;
+          float d[NCI][4];
+#pragma unroll
+          for (int kk = 0; kk < K; ++kk)
+#pragma unroll
+            for (int kc = 0; kc < KCO; ++kc) {
+              const float* ap = du_s + (8 * kc + 2 * ft) * TS + 4 + p0 + fg + H - kk;
+              const uint32_t a0 = __float_as_uint(ap[0]), a1 = __float_as_uint(ap[8]);
+              const uint32_t a2 = __float_as_uint(ap[TS]), a3 = __float_as_uint(ap[TS + 8]);
+#pragma unroll
+              for (int nt = 0; nt < NCI; ++nt) {
+                if (kk == 0 && kc == 0) cf_mma8_z(d[nt], a0, a1, a2, a3, wB[kk][kc][nt][0], wB[kk][kc][nt][1]);
+                else cf_mma8(d[nt], a0, a1, a2, a3, wB[kk][kc][nt][0], wB[kk][kc][nt][1]);
+              }
+            }
+          if constexpr (RES) {
+#pragma unroll
+            for (int kc = 0; kc < KCO; ++kc) {
+              const float* ap = yo_t + (8 * kc + 2 * ft) * TS + 4 + p0 + fg;
+              const uint32_t a0 = cf_rtf(ap[0]), a1 = cf_rtf(ap[8]), a2 = cf_rtf(ap[TS]), a3 = cf_rtf(ap[TS + 8]);
+#pragma unroll
+              for (int nt = 0; nt < NCI; ++nt) cf_mma8(d[nt], a0, a1, a2, a3, wR[kc][nt][0], wR[kc][nt][1]);
+            }
+          }
+          // thread holds (pos p0+fg | p0+fg+8, ci 8nt+2ft | +1)
+#pragma unroll
+          for (int nt = 0; nt < NCI; ++nt) {
+            const int ci = 8 * nt + 2 * ft;
+            if (ci >= cin) continue;
+            float* dst;
+            const float* add = nullptr;
+            int accf;
+            if (ci < a.c1) {
+              dst = a.dx1 ? a.dx1 + ((size_t)r * a.c1 + ci) * a.L : nullptr;
+              accf = a.acc1;
+              if (a.dadd) add = a.dadd + ((size_t)r * a.c1 + ci) * a.L;
+            } else {
+              dst = a.dx2 ? a.dx2 + ((size_t)r * a.c2 + (ci - a.c1)) * a.L : nullptr;
+              accf = a.acc2;
+            }
+            if (!dst) continue;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int l = tl0 + p0 + fg + 8 * hh;
+              if (l >= a.L) continue;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                float v = d[nt][2 * hh + i];
+                const size_t o = (size_t)i * a.L + l;
+                if (add) v += __ldg(add + o);
+                if (accf) v += dst[o];
+                dst[o] = v;
+              }
+            }
+          }
+        }
+      }
+    } else
     if (a.dx1 || a.dx2) {
       const int l = tl0 + P * tid;
       const bool ok = l < a.L;
@@ -832,6 +954,36 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
     }
 
     // ---------------------------------------------------------------- phase 3: dW[:, ci3, :] over this thread's segment
+    if constexpr (MMA) {
+      // dW_k[ci][co] += sum_pos x[ci][pos] du[co][pos + H - k]: A = x (rows ci, k-slots = 8 positions), B_k = shifted du
+      for (int chn = warp_; chn < TL / 8; chn += NW) {
+        const int p0 = 8 * chn;
+        uint32_t ax[MCI][4];
+#pragma unroll
+        for (int mt = 0; mt < MCI; ++mt) {
+          // rows >= cin of the m16 tile do not exist (their dW rows are dropped): re-read the last real row instead
+          const float* xp = x_t + min(16 * mt + fg, cin - 1) * TS + 4 + p0 + ft;
+          const float* xq = x_t + min(16 * mt + fg + 8, cin - 1) * TS + 4 + p0 + ft;
+          ax[mt][0] = cf_rtf(xp[0]); ax[mt][1] = cf_rtf(xq[0]); ax[mt][2] = cf_rtf(xp[4]); ax[mt][3] = cf_rtf(xq[4]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < KCO; ++nt) {
+          const float* bp = du_s + (8 * nt + fg) * TS + 4 + p0 + ft + H;
+#pragma unroll
+          for (int kk = 0; kk < K; ++kk) {
+            const uint32_t b0 = __float_as_uint(bp[-kk]), b1 = __float_as_uint(bp[4 - kk]);
+#pragma unroll
+            for (int mt = 0; mt < MCI; ++mt) cf_mma8(dWf[kk][mt][nt], ax[mt][0], ax[mt][1], ax[mt][2], ax[mt][3], b0, b1);
+          }
+          if constexpr (RES) {
+            const float* yp = yo_t + (8 * nt + fg) * TS + 4 + p0 + ft;
+            const uint32_t b0 = cf_rtf(yp[0]), b1 = cf_rtf(yp[4]);
+#pragma unroll
+            for (int mt = 0; mt < MCI; ++mt) cf_mma8(dRf[mt][nt], ax[mt][0], ax[mt][1], ax[mt][2], ax[mt][3], b0, b1);
+          }
+        }
+      }
+    } else
     if (p3_active) {
       const float* xr = x_t + ci3 * TS + 4;
       for (int q = q_begin; q < q_end; q += 4) {
@@ -862,6 +1014,21 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
 
   // ------------------------------------------------------------------ leave: parameter gradients
   if (EPI && cur_sample >= 0) flush_sample(cur_sample);
+  if constexpr (MMA) {   // thread holds dW_k[ci = 16mt + fg (+8)][co = 8nt + 2ft (+1)]
+#pragma unroll
+    for (int mt = 0; mt < MCI; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < KCO; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ci = 16 * mt + fg + 8 * (i >> 1), co = 8 * nt + 2 * ft + (i & 1);
+          if (ci < cin) {
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) atomicAdd(dw_s + (co * cin + ci) * K + kk, dWf[kk][mt][nt][i]);
+            if constexpr (RES) atomicAdd(dwres_s + co * cin + ci, dRf[mt][nt][i]);
+          }
+        }
+  } else
   if (p3_active) {
 #pragma unroll
     for (int co = 0; co < COUT; ++co)
@@ -878,7 +1045,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
   }
   for (int i = tid; i < COUT * cin * K; i += NT) atomicAdd(a.dw + i, dw_s[i]);
   if constexpr (RES) {
-    if (p3_active) {
+    if (!MMA && p3_active) {
 #pragma unroll
       for (int co = 0; co < COUT; ++co) atomicAdd(dwres_s + co * cin + ci3, dwres[co]);
     }
@@ -891,7 +1058,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
   }
 }
 
-template <int COUT, int K, int P, int NT, bool EPI, bool BULK, bool RES = false>
+template <int COUT, int K, int P, int NT, bool EPI, bool BULK, bool RES = false, int NCI = 0>
 static int launch_fused_tma(ConvBwdFusedArgs a, cudaStream_t st) {
   constexpr int TL = NT * P, TS = TL + 36, NW = NT / 32;
   const int cin = a.c1 + a.c2;
@@ -901,7 +1068,7 @@ static int launch_fused_tma(ConvBwdFusedArgs a, cudaStream_t st) {
   size_t smem = sizeof(float) * ((size_t)2 * rows * TS + (size_t)COUT * cin * 4 + (size_t)COUT * cin * K +
                                  (RES ? (size_t)2 * COUT * cin : 0) + NW * 2 * COUT) + 16;
   if (smem > 220 * 1024) return -6;
-  auto kern = conv_bwd_fused_tma_kernel<COUT, K, P, NT, EPI, BULK, RES>;
+  auto kern = conv_bwd_fused_tma_kernel<COUT, K, P, NT, EPI, BULK, RES, NCI>;
   static int sm_count = 0;
   if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -951,12 +1118,27 @@ static int dispatch_fused(const ConvBwdFusedArgs& a, int cout, cudaStream_t st) 
   if (mode < 0) { const char* e = getenv("DQ_CONV_BWD_NOTMA"); mode = (e && e[0] == '1') ? 1 : 0; }
   // the pipelined kernel covers: plain conv, or RMSNorm (+ scale/shift) + SiLU epilogue; channel counts in fours
   const bool epi_ok = !a.u || (a.g && a.act == 1);
+  const int cin = a.c1 + a.c2;
+  static int mma_mode = -1;   // DQ_CONV_BWD_MMA=0: FFMA contractions everywhere (cross-check)
+  if (mma_mode < 0) { const char* e = getenv("DQ_CONV_BWD_MMA"); mma_mode = (e && e[0] == '0') ? 0 : 1; }
+  const bool mma_on = mma_mode == 1;
+  if constexpr (K == 3) {
+    if (mode == 0 && mma_on && !a.dyo && al && a.L >= 128 && a.u && a.g && a.act == 1 && (a.c1 & 3) == 0 && (a.c2 & 3) == 0 &&
+        cout == 8 && cin <= 16) {
+      if (cin <= 8) return launch_fused_tma<8, 3, 2, 128, true, true, false, 1>(a, st);
+      return launch_fused_tma<8, 3, 2, 128, true, true, false, 2>(a, st);
+    }
+  }
   if (a.dyo) {   // conv3 + epilogue with the 1x1 res_conv over the same input: pipelined kernel only, COUT 4 / 8
     if constexpr (K == 3) {
       const bool al2 = al && (((size_t)a.dyo & 15) == 0);
       if (mode == 0 && al2 && a.L >= 128 && a.u && a.g && a.act == 1 && (a.c1 & 3) == 0 && (a.c2 & 3) == 0 && !a.dadd) {
         if (cout == 4) return launch_fused_tma<4, 3, 4, 128, true, true, true>(a, st);
-        if (cout == 8) return launch_fused_tma<8, 3, 2, 128, true, true, true>(a, st);
+        if (cout == 8) {
+          if (mma_on && cin <= 8) return launch_fused_tma<8, 3, 2, 128, true, true, true, 1>(a, st);
+          if (mma_on && cin <= 16) return launch_fused_tma<8, 3, 2, 128, true, true, true, 2>(a, st);
+          return launch_fused_tma<8, 3, 2, 128, true, true, true>(a, st);
+        }
       }
     }
     return 1;    // not covered: the caller runs the two convolutions separately

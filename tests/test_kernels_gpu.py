@@ -73,17 +73,19 @@ def test_resnet_block_fwd_bwd(ctx, pre, c1, c2, L):
     out, saved = net._resnet_fwd(pre, x1.cuda(), x2.cuda() if c2 else None, rt, True)
     assert rel_err(out, ref) < FP32_TOL
     dx1, dx2 = net._resnet_bwd(pre, saved, dout.cuda(), rt)
-    assert rel_err(dx1, x1r.grad) < FP32_TOL
+    # the 8-channel pipelined backward contracts on the tensor cores (TF32 operands, fp32 accumulate)
+    tol = TF32_TOL if (dout_shape_c == 8 and L % 4 == 0 and L >= 128) else FP32_TOL
+    assert rel_err(dx1, x1r.grad) < tol
     if c2:
-        assert rel_err(dx2, x2r.grad) < FP32_TOL
+        assert rel_err(dx2, x2r.grad) < tol
     for k, v in Pg.items():
         if k.endswith("mlp.1.weight") or k.endswith("mlp.1.bias"):
             continue
-        assert rel_err(net._params[k].grad, v.grad) < 2 * FP32_TOL, k
+        assert rel_err(net._params[k].grad, v.grad) < 2 * tol, k
     # d scale/shift -> compare through the Linear's bias gradient (= sum over samples of dSS)
     o = net.ss_off[pre + ".mlp.1"]
     n = Pg[pre + ".mlp.1.bias"].shape[0]
-    assert rel_err(net._dSS[:, o:o + n].sum(0), Pg[pre + ".mlp.1.bias"].grad) < 2 * FP32_TOL
+    assert rel_err(net._dSS[:, o:o + n].sum(0), Pg[pre + ".mlp.1.bias"].grad) < 2 * tol
 
 
 @pytest.mark.parametrize("pre,C,L", [("downs.0.2", 4, 320), ("downs.2.2", 8, 80), ("ups.0.2", 16, 5),
