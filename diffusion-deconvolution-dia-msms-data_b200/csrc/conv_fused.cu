@@ -38,6 +38,7 @@ struct ConvBwdFusedArgs {
   int c1, c2, R, L, rows_per_sample, ss_stride, act, acc1, acc2, tiles_per_row, total_tiles, tiles_per_cta;
   // optional second, 1x1 convolution over the same input (ResnetBlock.res_conv, unet1d.py:299/322): its output gradient
   // dyo (R, COUT, L), weight wres (COUT, cin); dx gets wres^T dyo added, dwres / dbres are accumulated
+  int al8 = 0;        // every tensor base is 8-byte aligned (set by the launcher)
   const float* dyo = nullptr;
   const float* wres = nullptr;
   float* dwres = nullptr;
@@ -445,8 +446,8 @@ __device__ __forceinline__ float cf_dsilu(float z) {
 template <int COUT, int K, int P, int NT, bool EPI, bool BULK, bool RES = false, int NCI = 0>
 __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs a) {
   constexpr bool MMA = NCI > 0;
-  static_assert(!MMA || (EPI && K == 3 && COUT % 8 == 0), "MMA variant: conv3 with epilogue, COUT in eights");
-  constexpr int KCO = COUT / 8 > 0 ? COUT / 8 : 1;       // k8 / n8 tiles over the output channels
+  static_assert(!MMA || (EPI && K == 3), "MMA variant: conv3 with epilogue");
+  constexpr int KCO = (COUT + 7) / 8;                    // k8 / n8 tiles over the output channels (rows >= COUT: zero weights)
   constexpr int MCI = (NCI + 1) / 2 > 0 ? (NCI + 1) / 2 : 1;   // m16 tiles over the input channels (phase 3)
   constexpr int TL = NT * P;
   constexpr int TS = TL + 36;
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
   float* stage0 = reinterpret_cast<float*>(dyn_smem4);
   const int stage_floats = rows * TS;
   float* w_s = stage0 + 2 * stage_floats;                // COUT * cin * 4
-  float* dw_s = w_s + COUT * cin * 4;                    // COUT * cin * K
+  float* dw_s = w_s + (MMA ? 0 : COUT * cin * 4);        // COUT * cin * K (MMA: weights live in fragments, no w_s)
   float* wres_s = dw_s + COUT * cin * K;                 // RES: COUT * cin
   float* dwres_s = wres_s + (RES ? COUT * cin : 0);      // RES: COUT * cin
   float* red = dwres_s + (RES ? COUT * cin : 0);         // NW * 2 * COUT
@@ -473,10 +474,11 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
     cf_mbar_init(bar1, BULK ? 1 : NT);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < COUT * cin * 4; i += NT) {
-    const int k = i & 3, pc = i >> 2;
-    w_s[i] = (k < K) ? a.w[(size_t)pc * K + k] : 0.f;
-  }
+  if (!MMA)
+    for (int i = tid; i < COUT * cin * 4; i += NT) {
+      const int k = i & 3, pc = i >> 2;
+      w_s[i] = (k < K) ? a.w[(size_t)pc * K + k] : 0.f;
+    }
   for (int i = tid; i < COUT * cin * K; i += NT) dw_s[i] = 0.f;
   if (RES)
     for (int i = tid; i < COUT * cin; i += NT) { wres_s[i] = a.wres[i]; dwres_s[i] = 0.f; }
@@ -490,11 +492,14 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
   // BULK: one lane per row issues that row's bulk copy; lane 0 posts the expected byte count first
   auto issue = [&](int tile, int s) {
     if (!BULK) {
+      // unaligned rows: one warp per row (the row pointer is computed once per warp and row), lanes stride over the
+      // elements with 8-byte copies when every row of the tensor starts 8-byte aligned (even L), else 4-byte ones
       const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
       const int l_lo = max(0, tl0 - 4), l_hi = min(a.L, tl0 + TL + 4);
       const int w = l_hi - l_lo, doff = l_lo - (tl0 - 4);
       float* st = stage0 + s * stage_floats;
-      for (int row = 0; row < rows; ++row) {
+      const bool even = ((a.L | w | l_lo) & 1) == 0 && a.al8;
+      for (int row = tid >> 5; row < rows; row += NW) {
         const float* src;
         if (row < COUT) src = a.dy + ((size_t)r * COUT + row) * a.L;
         else if (row < DYR) src = a.u + ((size_t)r * COUT + (row - COUT)) * a.L;
@@ -505,8 +510,13 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
         }
         src += l_lo;
         const uint32_t dst = cf_smem_u32(st + row * TS + doff);
-        for (int e = tid; e < w; e += NT)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (uint32_t)e), "l"(src + e) : "memory");
+        if (even) {
+          for (int e = (tid & 31) * 2; e < w; e += 64)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 4u * (uint32_t)e), "l"(src + e) : "memory");
+        } else {
+          for (int e = tid & 31; e < w; e += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (uint32_t)e), "l"(src + e) : "memory");
+        }
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(s ? bar1 : bar0) : "memory");
       return;
@@ -563,9 +573,10 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int co = 8 * kc + 2 * ft + i, ci = 8 * nt + fg;
+          const bool in = ci < cin && co < COUT;
 #pragma unroll
-          for (int kk = 0; kk < K; ++kk) wB[kk][kc][nt][i] = cf_tf32(ci < cin ? a.w[((size_t)co * cin + ci) * K + kk] : 0.f);
-          if constexpr (RES) wR[kc][nt][i] = cf_tf32(ci < cin ? a.wres[(size_t)co * cin + ci] : 0.f);
+          for (int kk = 0; kk < K; ++kk) wB[kk][kc][nt][i] = cf_tf32(in ? a.w[((size_t)co * cin + ci) * K + kk] : 0.f);
+          if constexpr (RES) wR[kc][nt][i] = cf_tf32(in ? a.wres[(size_t)co * cin + ci] : 0.f);
         }
 #pragma unroll
     for (int mt = 0; mt < MCI; ++mt)
@@ -802,6 +813,24 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
     if constexpr (MMA) {
       if (a.dx1 || a.dx2) {
         // warp w: slabs of 16 positions w, w + NW, ..; D[pos][ci] = sum_k A_k[pos][co] W_k[co][ci] (+ dyo wres)
+        // destination rows of this thread's channel pairs (ci = 8nt + 2ft, +1), fixed for the whole tile
+        float* dstp[NCI];
+        const float* addp[NCI];
+        bool accp[NCI];
+#pragma unroll
+        for (int nt = 0; nt < NCI; ++nt) {
+          const int ci = 8 * nt + 2 * ft;
+          dstp[nt] = nullptr; addp[nt] = nullptr; accp[nt] = false;
+          if (ci < a.c1) {
+            if (a.dx1) dstp[nt] = a.dx1 + ((size_t)r * a.c1 + ci) * a.L + tl0 + fg;
+            if (a.dadd) addp[nt] = a.dadd + ((size_t)r * a.c1 + ci) * a.L + tl0 + fg;
+            accp[nt] = a.acc1 != 0;
+          } else if (ci < cin) {
+            if (a.dx2) dstp[nt] = a.dx2 + ((size_t)r * a.c2 + (ci - a.c1)) * a.L + tl0 + fg;
+            accp[nt] = a.acc2 != 0;
+          }
+        }
+        const bool full = tl0 + TL <= a.L;   // CTA-uniform: no per-position bound checks
         for (int sl = warp_; sl < TL / 16; sl += NW) {
           const int p0 = 16 * sl;
           float d[NCI][4];
@@ -809,7 +838,8 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
           for (int kk = 0; kk < K; ++kk)
 #pragma unroll
             for (int kc = 0; kc < KCO; ++kc) {
-              const float* ap = du_s + (8 * kc + 2 * ft) * TS + 4 + p0 + fg + H - kk;
+              // channel rows >= COUT (COUT = 12) meet zero weights: any finite row will do
+              const float* ap = du_s + min(8 * kc + 2 * ft, COUT - 2) * TS + 4 + p0 + fg + H - kk;
               const uint32_t a0 = __float_as_uint(ap[0]), a1 = __float_as_uint(ap[8]);
               const uint32_t a2 = __float_as_uint(ap[TS]), a3 = __float_as_uint(ap[TS + 8]);
 #pragma unroll
@@ -821,42 +851,36 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
           if constexpr (RES) {
 #pragma unroll
             for (int kc = 0; kc < KCO; ++kc) {
-              const float* ap = yo_t + (8 * kc + 2 * ft) * TS + 4 + p0 + fg;
+              const float* ap = yo_t + min(8 * kc + 2 * ft, COUT - 2) * TS + 4 + p0 + fg;
               const uint32_t a0 = cf_rtf(ap[0]), a1 = cf_rtf(ap[8]), a2 = cf_rtf(ap[TS]), a3 = cf_rtf(ap[TS + 8]);
 #pragma unroll
               for (int nt = 0; nt < NCI; ++nt) cf_mma8(d[nt], a0, a1, a2, a3, wR[kc][nt][0], wR[kc][nt][1]);
             }
           }
           // thread holds (pos p0+fg | p0+fg+8, ci 8nt+2ft | +1)
+          const bool ok0 = full || tl0 + p0 + fg < a.L, ok1 = full || tl0 + p0 + fg + 8 < a.L;
 #pragma unroll
           for (int nt = 0; nt < NCI; ++nt) {
-            const int ci = 8 * nt + 2 * ft;
-            if (ci >= cin) continue;
-            float* dst;
-            const float* add = nullptr;
-            int accf;
-            if (ci < a.c1) {
-              dst = a.dx1 ? a.dx1 + ((size_t)r * a.c1 + ci) * a.L : nullptr;
-              accf = a.acc1;
-              if (a.dadd) add = a.dadd + ((size_t)r * a.c1 + ci) * a.L;
-            } else {
-              dst = a.dx2 ? a.dx2 + ((size_t)r * a.c2 + (ci - a.c1)) * a.L : nullptr;
-              accf = a.acc2;
-            }
-            if (!dst) continue;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const int l = tl0 + p0 + fg + 8 * hh;
-              if (l >= a.L) continue;
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                float v = d[nt][2 * hh + i];
-                const size_t o = (size_t)i * a.L + l;
-                if (add) v += __ldg(add + o);
-                if (accf) v += dst[o];
-                dst[o] = v;
+            if (!dstp[nt]) continue;   // warp-uniform per nt only when c1 is a multiple of 8; divergence is harmless
+            float* q0 = dstp[nt] + p0;
+            float* q1 = q0 + a.L;
+            if (addp[nt] || accp[nt]) {
+              float e[4] = {0.f, 0.f, 0.f, 0.f};
+              if (addp[nt]) {
+                const float* z0 = addp[nt] + p0;
+                const float* z1 = z0 + a.L;
+                if (ok0) { e[0] += __ldg(z0); e[1] += __ldg(z1); }
+                if (ok1) { e[2] += __ldg(z0 + 8); e[3] += __ldg(z1 + 8); }
               }
+              if (accp[nt]) {
+                if (ok0) { e[0] += q0[0]; e[1] += q1[0]; }
+                if (ok1) { e[2] += q0[8]; e[3] += q1[8]; }
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) d[nt][i] += e[i];
             }
+            if (ok0) { q0[0] = d[nt][0]; q1[0] = d[nt][1]; }
+            if (ok1) { q0[8] = d[nt][2]; q1[8] = d[nt][3]; }
           }
         }
       }
@@ -968,7 +992,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
         }
 #pragma unroll
         for (int nt = 0; nt < KCO; ++nt) {
-          const float* bp = du_s + (8 * nt + fg) * TS + 4 + p0 + ft + H;
+          const float* bp = du_s + min(8 * nt + fg, COUT - 1) * TS + 4 + p0 + ft + H;
 #pragma unroll
           for (int kk = 0; kk < K; ++kk) {
             const uint32_t b0 = __float_as_uint(bp[-kk]), b1 = __float_as_uint(bp[4 - kk]);
@@ -976,7 +1000,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
             for (int mt = 0; mt < MCI; ++mt) cf_mma8(dWf[kk][mt][nt], ax[mt][0], ax[mt][1], ax[mt][2], ax[mt][3], b0, b1);
           }
           if constexpr (RES) {
-            const float* yp = yo_t + (8 * nt + fg) * TS + 4 + p0 + ft;
+            const float* yp = yo_t + min(8 * nt + fg, COUT - 1) * TS + 4 + p0 + ft;
             const uint32_t b0 = cf_rtf(yp[0]), b1 = cf_rtf(yp[4]);
 #pragma unroll
             for (int mt = 0; mt < MCI; ++mt) cf_mma8(dRf[mt][nt], ax[mt][0], ax[mt][1], ax[mt][2], ax[mt][3], b0, b1);
@@ -1022,7 +1046,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int ci = 16 * mt + fg + 8 * (i >> 1), co = 8 * nt + 2 * ft + (i & 1);
-          if (ci < cin) {
+          if (ci < cin && co < COUT) {
 #pragma unroll
             for (int kk = 0; kk < K; ++kk) atomicAdd(dw_s + (co * cin + ci) * K + kk, dWf[kk][mt][nt][i]);
             if constexpr (RES) atomicAdd(dwres_s + co * cin + ci, dRf[mt][nt][i]);
@@ -1065,7 +1089,8 @@ static int launch_fused_tma(ConvBwdFusedArgs a, cudaStream_t st) {
   const int rows = (EPI ? 2 * COUT : COUT) + cin + (RES ? COUT : 0);
   a.tiles_per_row = (a.L + TL - 1) / TL;
   a.total_tiles = a.tiles_per_row * a.R;
-  size_t smem = sizeof(float) * ((size_t)2 * rows * TS + (size_t)COUT * cin * 4 + (size_t)COUT * cin * K +
+  a.al8 = ((((size_t)a.dy | (size_t)a.u | (size_t)a.x1 | (size_t)a.x2 | (size_t)a.dyo) & 7) == 0) ? 1 : 0;
+  size_t smem = sizeof(float) * ((size_t)2 * rows * TS + (NCI > 0 ? 0 : (size_t)COUT * cin * 4) + (size_t)COUT * cin * K +
                                  (RES ? (size_t)2 * COUT * cin : 0) + NW * 2 * COUT) + 16;
   if (smem > 220 * 1024) return -6;
   auto kern = conv_bwd_fused_tma_kernel<COUT, K, P, NT, EPI, BULK, RES, NCI>;
@@ -1122,22 +1147,39 @@ static int dispatch_fused(const ConvBwdFusedArgs& a, int cout, cudaStream_t st) 
   static int mma_mode = -1;   // DQ_CONV_BWD_MMA=0: FFMA contractions everywhere (cross-check)
   if (mma_mode < 0) { const char* e = getenv("DQ_CONV_BWD_MMA"); mma_mode = (e && e[0] == '0') ? 0 : 1; }
   const bool mma_on = mma_mode == 1;
+  const bool ch4 = (a.c1 & 3) == 0 && (a.c2 & 3) == 0;
   if constexpr (K == 3) {
-    if (mode == 0 && mma_on && !a.dyo && al && a.L >= 128 && a.u && a.g && a.act == 1 && (a.c1 & 3) == 0 && (a.c2 & 3) == 0 &&
-        cout == 8 && cin <= 16) {
-      if (cin <= 8) return launch_fused_tma<8, 3, 2, 128, true, true, false, 1>(a, st);
-      return launch_fused_tma<8, 3, 2, 128, true, true, false, 2>(a, st);
+    // conv3 + RMSNorm / SiLU epilogue at 8 .. 16 channels: tensor-core contractions (NCI = n8 tiles over cin)
+    if (mode == 0 && mma_on && !a.dyo && a.L >= 128 && a.u && a.g && a.act == 1 && ch4 && cin <= 32) {
+      const int nci = (cin + 7) / 8;
+      if (al) {
+        if (cout == 8 && nci == 1) return launch_fused_tma<8, 3, 2, 128, true, true, false, 1>(a, st);
+        if (cout == 8 && nci == 2) return launch_fused_tma<8, 3, 2, 128, true, true, false, 2>(a, st);
+        if (cout == 12 && nci == 2) return launch_fused_tma<12, 3, 2, 128, true, true, false, 2>(a, st);
+        if (cout == 16 && nci == 2) return launch_fused_tma<16, 3, 1, 128, true, true, false, 2>(a, st);
+      } else {
+        if (cout == 12 && nci == 2) return launch_fused_tma<12, 3, 1, 128, true, false, false, 2>(a, st);
+        if (cout == 16 && nci == 2) return launch_fused_tma<16, 3, 1, 128, true, false, false, 2>(a, st);
+      }
     }
   }
-  if (a.dyo) {   // conv3 + epilogue with the 1x1 res_conv over the same input: pipelined kernel only, COUT 4 / 8
+  if (a.dyo) {   // conv3 + epilogue with the 1x1 res_conv over the same input: pipelined kernel only
     if constexpr (K == 3) {
       const bool al2 = al && (((size_t)a.dyo & 15) == 0);
-      if (mode == 0 && al2 && a.L >= 128 && a.u && a.g && a.act == 1 && (a.c1 & 3) == 0 && (a.c2 & 3) == 0 && !a.dadd) {
-        if (cout == 4) return launch_fused_tma<4, 3, 4, 128, true, true, true>(a, st);
-        if (cout == 8) {
-          if (mma_on && cin <= 8) return launch_fused_tma<8, 3, 2, 128, true, true, true, 1>(a, st);
-          if (mma_on && cin <= 16) return launch_fused_tma<8, 3, 2, 128, true, true, true, 2>(a, st);
-          return launch_fused_tma<8, 3, 2, 128, true, true, true>(a, st);
+      if (mode == 0 && a.L >= 128 && a.u && a.g && a.act == 1 && ch4 && !a.dadd) {
+        const int nci = (cin + 7) / 8;
+        if (al2) {
+          if (cout == 4) return launch_fused_tma<4, 3, 4, 128, true, true, true>(a, st);
+          if (cout == 8) {
+            if (mma_on && nci == 1) return launch_fused_tma<8, 3, 2, 128, true, true, true, 1>(a, st);
+            if (mma_on && nci == 2) return launch_fused_tma<8, 3, 2, 128, true, true, true, 2>(a, st);
+            return launch_fused_tma<8, 3, 2, 128, true, true, true>(a, st);
+          }
+          if (mma_on && cout == 12 && nci == 3) return launch_fused_tma<12, 3, 1, 128, true, true, true, 3>(a, st);
+          if (mma_on && cout == 16 && nci == 4) return launch_fused_tma<16, 3, 1, 128, true, true, true, 4>(a, st);
+        } else if (mma_on) {
+          if (cout == 12 && nci == 3) return launch_fused_tma<12, 3, 1, 128, true, false, true, 3>(a, st);
+          if (cout == 16 && nci == 4) return launch_fused_tma<16, 3, 1, 128, true, false, true, 4>(a, st);
         }
       }
     }
@@ -1225,14 +1267,14 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
       const int l_lo = max(0, x0 - 4), l_hi = min(Lx, x0 + xw_ + 4);
       const int w = l_hi - l_lo, doff = l_lo - (x0 - 4);
       float* st = stage0 + s * stage_floats;
-      for (int row = 0; row < rows; ++row) {
+      for (int row = tid >> 5; row < rows; row += NT / 32) {   // one warp per row: the row pointer is computed once per warp
         const float* src;
         if (row < a.c1) src = a.x1 + ((size_t)r * a.c1 + row) * Lx;
         else if (row < cin) src = a.x2 + ((size_t)r * a.c2 + (row - a.c1)) * Lx;
         else src = a.res + ((size_t)r * COUT + (row - cin)) * a.L;
         src += l_lo;
         const uint32_t dst = cf_smem_u32(st + row * TS + doff);
-        for (int e = tid; e < w; e += NT)
+        for (int e = tid & 31; e < w; e += 32)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (uint32_t)e), "l"(src + e) : "memory");
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(s ? bar1 : bar0) : "memory");
@@ -1496,10 +1538,10 @@ __global__ void __launch_bounds__(NT) resblock_fwd_tma_kernel(ResFwdArgs a) {
     float* st = stage0 + s * stage_floats;
     if (!BULK) {
       const int w = l_hi - l_lo, doff = l_lo - (tl0 - 4);
-      for (int row = 0; row < cin; ++row) {
+      for (int row = tid >> 5; row < cin; row += NT / 32) {   // one warp per row
         const float* src = (row < a.c1 ? a.x1 + ((size_t)r * a.c1 + row) * a.L : a.x2 + ((size_t)r * a.c2 + (row - a.c1)) * a.L) + l_lo;
         const uint32_t dst = cf_smem_u32(st + row * TS + doff);
-        for (int e = tid; e < w; e += NT)
+        for (int e = tid & 31; e < w; e += 32)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (uint32_t)e), "l"(src + e) : "memory");
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(s ? bar1 : bar0) : "memory");

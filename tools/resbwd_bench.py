@@ -28,7 +28,8 @@ def tm(fn, reps=5):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1000
 for pre, c1, c2, L in [("downs.0.0", 4, 0, 40000), ("ups.6.0", 4, 4, 40000), ("ups.5.0", 8, 4, 20000), ("downs.2.0", 8, 0, 10000),
-                       ("ups.4.0", 8, 8, 10000), ("ups.3.0", 12, 8, 5000)]:
+                       ("ups.4.0", 8, 8, 10000), ("ups.3.0", 12, 8, 5000), ("downs.4.0", 12, 0, 2500), ("ups.2.0", 12, 12, 2500),
+                       ("downs.5.0", 12, 0, 1250), ("ups.1.0", 16, 12, 1250), ("downs.6.0", 16, 0, 625), ("ups.0.0", 16, 16, 625)]:
     x1 = torch.randn(R, c1, L, device="cuda"); x2 = torch.randn(R, c2, L, device="cuda") if c2 else None
     cout = net.specs[pre + ".block1.proj.weight"][0]
     out, saved = net._resnet_fwd(pre, x1, x2, rt, True)
