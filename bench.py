@@ -329,7 +329,7 @@ def main():
         line = {
             "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16 (mid-stage tcgen05 GEMMs, fp32 accumulate) / tf32 (linear-attention mma.sync, fp32 accumulate) / f32 elsewhere",
+            "vs_baseline": None, "dtype": "bf16 (mid-stage tcgen05 GEMMs, fp32 accumulate) / tf32 (linear-attention and 8-16-channel conv-backward mma.sync, fp32 accumulate) / f32 elsewhere",
             "data": "synthetic", "config": workload_config(world, args.micro_batch, B),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
@@ -406,8 +406,21 @@ def dominant_kernel_roofline(torch, N, net, dev, n_samples=64):
     others.append({"kernel": "dq_conv_bwd_fused (conv_bwd_fused_tma_kernel<4,3>: epilogue bwd + dgrad + wgrad), level 0",
                    "bound": "hbm", "achieved": by / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                    "frac": by / (ms * 1e-3) / 1e9 / pk["hbm"], "ms_per_launch": ms})
-    net._dSS = None
     del x1, y, u, dy
+    # ---- ResnetBlock backward on the up path at 8 channels (ups.4.0: 16 -> 8, L = 10000): block2, then block1 fused with
+    # the 1x1 res_conv; dgrad / wgrad contractions on mma.sync TF32 tensor cores inside the HBM pipeline
+    pre, c1, c2, L8 = "ups.4.0", 8, 8, 10000
+    xa = torch.randn(R, c1, L8, device=dev)
+    xb = torch.randn(R, c2, L8, device=dev)
+    o8, saved8 = net._resnet_fwd(pre, xa, xb, RT, True)
+    d8 = torch.randn_like(o8)
+    ms = _time_ms(torch, lambda: net._resnet_bwd(pre, saved8, d8, RT))
+    by = (7 * 8 + 2 * 16) * 4.0 * R * L8   # dout, u2, h1 -> dh1 | dh1, u1, x, dout -> dx
+    others.append({"kernel": "ResnetBlock backward ups.4.0 (2 x conv_bwd_fused_tma_kernel<8,3>, TF32 mma.sync contractions, "
+                             "res_conv fused), L = 10000", "bound": "hbm", "achieved": by / (ms * 1e-3) / 1e9,
+                   "peak": pk["hbm"], "unit": "GB/s", "frac": by / (ms * 1e-3) / 1e9 / pk["hbm"], "ms_per_launch": ms})
+    net._dSS = None
+    del xa, xb, o8, saved8, d8
     # ---- mid-stage tcgen05 GEMMs (M = 32 x 36 padded rows, N = 10000, K = 3 x 10000)
     Nm, Mp = net.mid_channels, n_samples * (RT + 2)
     A = torch.randn(Mp, Nm, device=dev).bfloat16()

@@ -10,11 +10,11 @@ want = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_
         'lts__t_bytes.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__inst_executed.sum']
 want += [h for h in hdr if h.startswith('smsp__average_warps_issue_stalled') and h.endswith('per_issue_active.ratio')]
 idx = {h: i for i, h in enumerate(hdr)}
-names = [r[idx['Kernel Name']][:22] for r in rows[2:]]
+names = [r[idx['Kernel Name']].replace('void ', '').replace('dq::', '')[:60] for r in rows[2:]]
 print(' ' * 52, names)
 for w in want:
     if w in idx:
-        vals = [r[idx[w]][:9] for r in rows[2:]]
+        vals = [r[idx[w]][:14] for r in rows[2:]]
         if w.startswith('smsp__average_warps') and all(float(v or 0) < 0.15 for v in vals):
             continue
         print(f"{w.replace('smsp__average_warps_issue_stalled_','stall:').replace('_per_issue_active.ratio','')[:52]:52s}", vals, units[idx[w]])
