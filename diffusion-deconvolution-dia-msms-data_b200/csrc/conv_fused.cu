@@ -1817,6 +1817,303 @@ static int launch_resblock(ResFwdArgs a, cudaStream_t st) {
   return 0;
 }
 
+
+// =====================================================================================================================
+// Tensor-core form of the fused ResnetBlock forward for 8 / 12 / 16 channels (where 3 * cin * COUT FMAs per position and
+// conv bound the FFMA kernel above: 25-60 % of HBM).  Same staging pipeline; a warp owns slabs of 16 positions and keeps
+// everything in mma.sync m16n8k8 (TF32 operands, fp32 accumulate) fragment layout:
+//   block 1: U1[pos][co] = b1 + sum_k X_k[pos][ci] W1_k[ci][co]  -> RMSNorm over co (quad shuffle) -> scale/shift -> SiLU
+//            -> h1 tile in shared memory (TF32-rounded; the unrounded values go to the saved h1)
+//   block 2: U2 = b2 + sum_k H1_k W2_k -> RMSNorm -> SiLU, + skip (1x1 conv of x as one more MMA chain, or x itself)
+// k-slots are permuted (slot t <-> channel 2t, t+4 <-> 2t+1): with TS = 4 (mod 32) every fragment access is conflict-free.
+// The two halo positions of the h1 tile are evaluated by one warp in fp32 FFMA (as in the kernel above).
+template <int COUT, int KCI, int TL, int NT, bool BULK>
+__global__ void __launch_bounds__(NT) resblock_fwd_mma_kernel(ResFwdArgs a) {
+  constexpr int TS = TL + 36;
+  constexpr int NW = NT / 32;
+  constexpr int KCO = (COUT + 7) / 8;
+  extern __shared__ float4 dyn_smem4[];
+  const int cin = a.c1 + a.c2;
+  const bool has_res = a.wres != nullptr;
+  float* stage0 = reinterpret_cast<float*>(dyn_smem4);
+  const int stage_floats = cin * TS;
+  float* h1_s = stage0 + 2 * stage_floats;                // COUT * TS   (position p at index p + 4)
+  float* w1_s = h1_s + COUT * TS;                         // [(ci*3 + k) * COUT + co]   (halo evaluation only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w1_s + ((cin * 3 * COUT + 3) & ~3));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, fg = lane >> 2, ft = lane & 3;
+  const uint32_t bar0 = cf_smem_u32(bars), bar1 = bar0 + 8;
+  if (tid == 0) {
+    cf_mbar_init(bar0, BULK ? 1 : NT);
+    cf_mbar_init(bar1, BULK ? 1 : NT);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < cin * 3 * COUT; i += NT) { const int co = i % COUT, ck = i / COUT; w1_s[i] = a.w1[(size_t)co * cin * 3 + ck]; }
+  for (int i = tid; i < COUT * TS; i += NT) h1_s[i] = 0.f;
+  for (int i = tid; i < 2 * stage_floats; i += NT) stage0[i] = 0.f;   // slots no copy fills stay finite
+  // weight fragments (B operands): b0 = W[co = 8nt + fg][c = 8kc + 2ft], b1 = W[co][c + 1]
+  uint32_t W1f[3][KCI][KCO][2], W2f[3][KCO][KCO][2], Wrf[KCI][KCO][2];
+  float bias1[KCO][2], bias2[KCO][2], biasr[KCO][2], gg1[KCO][2], gg2[KCO][2];
+  const float sqrtC = sqrtf((float)COUT);
+#pragma unroll
+  for (int nt = 0; nt < KCO; ++nt) {
+    const int co = 8 * nt + fg;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+      for (int kc = 0; kc < KCI; ++kc) {
+        const int ci = 8 * kc + 2 * ft + i;
+        const bool in = ci < cin && co < COUT;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) W1f[k][kc][nt][i] = cf_tf32(in ? a.w1[((size_t)co * cin + ci) * 3 + k] : 0.f);
+        Wrf[kc][nt][i] = cf_tf32(in && has_res ? a.wres[(size_t)co * cin + ci] : 0.f);
+      }
+#pragma unroll
+      for (int kc = 0; kc < KCO; ++kc) {
+        const int c = 8 * kc + 2 * ft + i;
+        const bool in = c < COUT && co < COUT;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) W2f[k][kc][nt][i] = cf_tf32(in ? a.w2[((size_t)co * COUT + c) * 3 + k] : 0.f);
+      }
+      // per-thread channel constants of the accumulator columns co' = 8nt + 2ft + i
+      const int cq = 8 * nt + 2 * ft + i;
+      const bool inq = cq < COUT;
+      bias1[nt][i] = inq ? a.b1[cq] : 0.f;
+      bias2[nt][i] = inq ? a.b2[cq] : 0.f;
+      biasr[nt][i] = (inq && has_res && a.bres) ? a.bres[cq] : 0.f;
+      gg1[nt][i] = inq ? a.g1[cq] * sqrtC : 0.f;
+      gg2[nt][i] = inq ? a.g2[cq] * sqrtC : 0.f;
+    }
+  }
+  __syncthreads();
+  const int t_begin = blockIdx.x * a.tiles_per_cta, t_end = min(a.total_tiles, t_begin + a.tiles_per_cta);
+  const int n_tiles = t_end - t_begin;
+
+  auto issue = [&](int tile, int s) {
+    const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
+    const int l_lo = max(0, tl0 - 4), l_hi = min(a.L, tl0 + TL + 4);
+    float* st = stage0 + s * stage_floats;
+    if (!BULK) {
+      const int w = l_hi - l_lo, doff = l_lo - (tl0 - 4);
+      for (int row = warp; row < cin; row += NW) {   // one warp per row
+        const float* src = (row < a.c1 ? a.x1 + ((size_t)r * a.c1 + row) * a.L : a.x2 + ((size_t)r * a.c2 + (row - a.c1)) * a.L) + l_lo;
+        const uint32_t dst = cf_smem_u32(st + row * TS + doff);
+        for (int e = lane; e < w; e += 32)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (uint32_t)e), "l"(src + e) : "memory");
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(s ? bar1 : bar0) : "memory");
+      return;
+    }
+    if (tid < 32) {
+      const uint32_t bytes = (uint32_t)(l_hi - l_lo) * 4u;
+      const uint32_t bar = s ? bar1 : bar0;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (tid == 0) cf_mbar_expect_tx(bar, bytes * (uint32_t)cin);
+      __syncwarp();
+      for (int row = tid; row < cin; row += 32) {
+        const float* src = row < a.c1 ? a.x1 + ((size_t)r * a.c1 + row) * a.L : a.x2 + ((size_t)r * a.c2 + (row - a.c1)) * a.L;
+        cf_bulk_g2s(cf_smem_u32(st + row * TS + (l_lo - (tl0 - 4))), src + l_lo, bytes, bar);
+      }
+    }
+  };
+  if (n_tiles > 0) issue(t_begin, 0);
+  if (n_tiles > 1) issue(t_begin + 1, 1);
+
+  const bool has_ss = a.ss != nullptr;
+  float gs1[KCO][2], sh1[KCO][2];
+  int cur_sample = -1;
+
+  // fragment (rows = positions p0 + fg, + 8; columns = channels 8nt + 2ft, + 1) -> (R, COUT, L) tensor
+  auto store_frag = [&](float* dst, const float (&v)[KCO][4], bool ok0, bool ok1) {
+#pragma unroll
+    for (int nt = 0; nt < KCO; ++nt) {
+      if (8 * nt + 2 * ft < COUT) {
+        float* q = dst + (size_t)(8 * nt + 2 * ft) * a.L;
+        if (ok0) { q[0] = v[nt][0]; q[a.L] = v[nt][1]; }
+        if (ok1) { q[8] = v[nt][2]; q[a.L + 8] = v[nt][3]; }
+      }
+    }
+  };
+  // RMSNorm over the COUT channels of rows fg / fg + 8 of a fragment set: 1 / max(||u||, 1e-12)
+  auto inv_norm = [&](const float (&v)[KCO][4], float& inv0, float& inv1) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < KCO; ++nt) {
+      s0 = fmaf(v[nt][0], v[nt][0], fmaf(v[nt][1], v[nt][1], s0));
+      s1 = fmaf(v[nt][2], v[nt][2], fmaf(v[nt][3], v[nt][3], s1));
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    inv0 = s0 > 1e-24f ? cf_rsqrt(s0) : 1e12f;
+    inv1 = s1 > 1e-24f ? cf_rsqrt(s1) : 1e12f;
+  };
+
+  for (int it = 0; it < n_tiles; ++it) {
+    const int tile = t_begin + it, s = it & 1;
+    const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
+    const int sample = r / a.rows_per_sample;
+    if (sample != cur_sample) {
+      cur_sample = sample;
+#pragma unroll
+      for (int nt = 0; nt < KCO; ++nt)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int cq = 8 * nt + 2 * ft + i;
+          const bool inq = cq < COUT && has_ss;
+          gs1[nt][i] = gg1[nt][i] * (inq ? a.ss[(size_t)sample * a.ss_stride + cq] + 1.f : 1.f);
+          sh1[nt][i] = inq ? a.ss[(size_t)sample * a.ss_stride + COUT + cq] : 0.f;
+        }
+    }
+    float* x_t = stage0 + s * stage_floats;
+    cf_mbar_wait(s ? bar1 : bar0, (uint32_t)((it >> 1) & 1));
+    // conv zero padding at the row ends (positions -1 and L) wherever they fall inside the staged window
+    const bool edge = tl0 == 0 || a.L < tl0 + TL + 4;
+    if (edge) {
+      if (tid < cin) {
+        if (tl0 == 0) x_t[tid * TS + 3] = 0.f;
+        if (a.L < tl0 + TL + 4) x_t[tid * TS + (a.L - tl0 + 4)] = 0.f;
+      }
+      __syncthreads();
+    }
+    const size_t rbase = (size_t)r * COUT * a.L + tl0 + fg;
+    const bool full = tl0 + TL <= a.L;
+
+    // ------------------------------------------------------------ block 1 -> h1 tile
+    for (int sl = warp; sl < TL / 16; sl += NW) {
+      const int p0 = 16 * sl;
+      const bool ok0 = full || tl0 + p0 + fg < a.L, ok1 = full || tl0 + p0 + fg + 8 < a.L;
+      float u[KCO][4];
+#pragma unroll
+      for (int nt = 0; nt < KCO; ++nt) { u[nt][0] = u[nt][2] = bias1[nt][0]; u[nt][1] = u[nt][3] = bias1[nt][1]; }
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int kc = 0; kc < KCI; ++kc) {
+          const float* ap = x_t + min(8 * kc + 2 * ft, cin - 2) * TS + 4 + p0 + fg + k - 1;
+          const uint32_t a0 = cf_rtf(ap[0]), a1 = cf_rtf(ap[8]), a2 = cf_rtf(ap[TS]), a3 = cf_rtf(ap[TS + 8]);
+#pragma unroll
+          for (int nt = 0; nt < KCO; ++nt) cf_mma8(u[nt], a0, a1, a2, a3, W1f[k][kc][nt][0], W1f[k][kc][nt][1]);
+        }
+      if (a.u1) store_frag(a.u1 + rbase + p0, u, ok0, ok1);
+      float inv0, inv1;
+      inv_norm(u, inv0, inv1);
+#pragma unroll
+      for (int nt = 0; nt < KCO; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float z = fmaf(u[nt][i] * (i < 2 ? inv0 : inv1), gs1[nt][i & 1], sh1[nt][i & 1]);
+          z = z * cf_rcp(1.f + cf_ex2(-1.4426950408889634f * z));
+          u[nt][i] = ((i < 2) ? ok0 : ok1) ? z : 0.f;       // conv2 sees zero padding beyond the row end
+        }
+      if (a.h1) store_frag(a.h1 + rbase + p0, u, ok0, ok1);
+#pragma unroll
+      for (int nt = 0; nt < KCO; ++nt)
+        if (8 * nt + 2 * ft < COUT) {
+          float* hp = h1_s + (8 * nt + 2 * ft) * TS + 4 + p0 + fg;
+          hp[0] = __uint_as_float(cf_rtf(u[nt][0])); hp[TS] = __uint_as_float(cf_rtf(u[nt][1]));
+          hp[8] = __uint_as_float(cf_rtf(u[nt][2])); hp[TS + 8] = __uint_as_float(cf_rtf(u[nt][3]));
+        }
+    }
+    if (tid < 32) {
+      // h1 at the two halo positions tl0 - 1 (lanes 0-15) and tl0 + TL (lanes 16-31): one output channel per lane
+      const int side = tid >> 4, c = tid & 15;
+      const int idx = side == 0 ? 3 : TL + 4;
+      const int lp = tl0 - 4 + idx;
+      const bool ok = lp >= 0 && lp < a.L;
+      const int cc = c < COUT ? c : 0;
+      float acc = a.b1[cc];
+      for (int ci = 0; ci < cin; ++ci) {
+        const float* xr = x_t + ci * TS + idx;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc = fmaf(xr[k - 1], w1_s[(ci * 3 + k) * COUT + cc], acc);
+      }
+      if (c >= COUT) acc = 0.f;
+      float s2 = acc * acc;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      const float inv = s2 > 1e-24f ? cf_rsqrt(s2) : 1e12f;
+      const float sc1 = has_ss ? a.ss[(size_t)sample * a.ss_stride + cc] + 1.f : 1.f;
+      const float shc = has_ss ? a.ss[(size_t)sample * a.ss_stride + COUT + cc] : 0.f;
+      float z = fmaf(acc * inv, a.g1[cc] * sqrtC * sc1, shc);
+      z = z * cf_rcp(1.f + cf_ex2(-1.4426950408889634f * z));
+      if (c < COUT) h1_s[c * TS + idx] = ok ? __uint_as_float(cf_rtf(z)) : 0.f;
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------ block 2 + skip -> out
+    for (int sl = warp; sl < TL / 16; sl += NW) {
+      const int p0 = 16 * sl;
+      const bool ok0 = full || tl0 + p0 + fg < a.L, ok1 = full || tl0 + p0 + fg + 8 < a.L;
+      float u[KCO][4];
+#pragma unroll
+      for (int nt = 0; nt < KCO; ++nt) { u[nt][0] = u[nt][2] = bias2[nt][0]; u[nt][1] = u[nt][3] = bias2[nt][1]; }
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int kc = 0; kc < KCO; ++kc) {
+          const float* ap = h1_s + min(8 * kc + 2 * ft, COUT - 2) * TS + 4 + p0 + fg + k - 1;
+          const uint32_t a0 = __float_as_uint(ap[0]), a1 = __float_as_uint(ap[8]);
+          const uint32_t a2 = __float_as_uint(ap[TS]), a3 = __float_as_uint(ap[TS + 8]);
+#pragma unroll
+          for (int nt = 0; nt < KCO; ++nt) cf_mma8(u[nt], a0, a1, a2, a3, W2f[k][kc][nt][0], W2f[k][kc][nt][1]);
+        }
+      if (a.u2) store_frag(a.u2 + rbase + p0, u, ok0, ok1);
+      float inv0, inv1;
+      inv_norm(u, inv0, inv1);
+      float sk[KCO][4];
+      if (has_res) {   // CTA-uniform
+#pragma unroll
+        for (int nt = 0; nt < KCO; ++nt) { sk[nt][0] = sk[nt][2] = biasr[nt][0]; sk[nt][1] = sk[nt][3] = biasr[nt][1]; }
+#pragma unroll
+        for (int kc = 0; kc < KCI; ++kc) {
+          const float* ap = x_t + min(8 * kc + 2 * ft, cin - 2) * TS + 4 + p0 + fg;
+          const uint32_t a0 = cf_rtf(ap[0]), a1 = cf_rtf(ap[8]), a2 = cf_rtf(ap[TS]), a3 = cf_rtf(ap[TS + 8]);
+#pragma unroll
+          for (int nt = 0; nt < KCO; ++nt) cf_mma8(sk[nt], a0, a1, a2, a3, Wrf[kc][nt][0], Wrf[kc][nt][1]);
+        }
+      } else {         // identity skip (cin == COUT): exact fp32 x
+#pragma unroll
+        for (int nt = 0; nt < KCO; ++nt) {
+          const float* xp = x_t + min(8 * nt + 2 * ft, COUT - 2) * TS + 4 + p0 + fg;
+          sk[nt][0] = xp[0]; sk[nt][1] = xp[TS]; sk[nt][2] = xp[8]; sk[nt][3] = xp[TS + 8];
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < KCO; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float z = u[nt][i] * (i < 2 ? inv0 : inv1) * gg2[nt][i & 1];
+          u[nt][i] = z * cf_rcp(1.f + cf_ex2(-1.4426950408889634f * z)) + sk[nt][i];
+        }
+      store_frag(a.out + rbase + p0, u, ok0, ok1);
+    }
+    __syncthreads();   // everyone is done with stage s and the h1 tile
+    if (it + 2 < n_tiles) issue(tile + 2, s);
+  }
+}
+
+template <int COUT, int KCI, int TL, int NT, bool BULK>
+static int launch_resblock_mma(ResFwdArgs a, cudaStream_t st) {
+  constexpr int TS = TL + 36;
+  const int cin = a.c1 + a.c2;
+  a.tiles_per_row = (a.L + TL - 1) / TL;
+  a.total_tiles = a.tiles_per_row * a.R;
+  size_t smem = sizeof(float) * ((size_t)2 * cin * TS + (size_t)COUT * TS + (size_t)((cin * 3 * COUT + 3) & ~3)) + 32;
+  if (smem > 220 * 1024) return -6;
+  auto kern = resblock_fwd_mma_kernel<COUT, KCI, TL, NT, BULK>;
+  static int sm_count = 0;
+  if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+  if (occ < 1) return -6;
+  int grid = min(a.total_tiles, sm_count * occ);
+  a.tiles_per_cta = (a.total_tiles + grid - 1) / grid;
+  grid = (a.total_tiles + a.tiles_per_cta - 1) / a.tiles_per_cta;
+  kern<<<(unsigned)grid, NT, smem, st>>>(a);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace dq
 
 using namespace dq;
@@ -1868,6 +2165,24 @@ DQ_API int dq_resblock_fwd(const float* x1, int c1, const float* x2, int c2, con
   ResFwdArgs a{x1, x2, w1, b1, g1, ss, w2, b2, g2, wres, bres, u1, h1, u2, out, c1, c2, R, L, rows_per_sample, ss_stride, 0, 0, 0};
   const bool al = (L % 4 == 0) && ((((size_t)x1 | (size_t)x2 | (size_t)u1 | (size_t)h1 | (size_t)u2 | (size_t)out) & 15) == 0);
   cudaStream_t st = (cudaStream_t)stream;
+  static int mma_mode = -1;   // DQ_RESBLOCK_MMA=0: FFMA kernels at every channel count (cross-check)
+  if (mma_mode < 0) { const char* e = getenv("DQ_RESBLOCK_MMA"); mma_mode = (e && e[0] == '0') ? 0 : 1; }
+  if (mma_mode && cout >= 8) {
+    const int kci = (cin + 7) / 8;
+    if (al) {
+      // (cout 8, cin 8: the FFMA2 kernel is as fast — 6 warp-instructions per position of conv work either way)
+      if (cout == 8 && kci == 2) return launch_resblock_mma<8, 2, 256, 128, true>(a, st);
+      if (cout == 12 && kci == 2) return launch_resblock_mma<12, 2, 256, 128, true>(a, st);
+      if (cout == 12 && kci == 3) return launch_resblock_mma<12, 3, 256, 128, true>(a, st);
+      if (cout == 16 && kci == 2) return launch_resblock_mma<16, 2, 128, 128, true>(a, st);
+      if (cout == 16 && kci == 4) return launch_resblock_mma<16, 4, 128, 128, true>(a, st);
+    } else {
+      if (cout == 12 && kci == 2) return launch_resblock_mma<12, 2, 128, 128, false>(a, st);
+      if (cout == 12 && kci == 3) return launch_resblock_mma<12, 3, 128, 128, false>(a, st);
+      if (cout == 16 && kci == 2) return launch_resblock_mma<16, 2, 128, 128, false>(a, st);
+      if (cout == 16 && kci == 4) return launch_resblock_mma<16, 4, 128, 128, false>(a, st);
+    }
+  }
   switch (cout) {
     case 4: return al ? launch_resblock<4, 4, 128, true>(a, st) : launch_resblock<4, 4, 128, false>(a, st);
     case 8: return al ? launch_resblock<8, 4, 128, true>(a, st) : launch_resblock<8, 2, 128, false>(a, st);

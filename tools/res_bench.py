@@ -16,7 +16,7 @@ def tm(fn, reps=5):
     for _ in range(reps): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1000
-for pre, c1, c2, L in [("downs.0.0", 4, 0, 40000), ("ups.6.0", 4, 4, 40000), ("downs.2.0", 8, 0, 10000), ("ups.4.0", 8, 8, 10000), ("downs.4.0", 12, 0, 2500)]:
+for pre, c1, c2, L in [("downs.0.0", 4, 0, 40000), ("ups.6.0", 4, 4, 40000), ("downs.2.0", 8, 0, 10000), ("ups.4.0", 8, 8, 10000), ("downs.4.0", 12, 0, 2500), ("ups.2.0", 12, 12, 2500), ("ups.1.0", 16, 12, 1250), ("downs.6.0", 16, 0, 625)]:
     x1 = torch.randn(R, c1, L, device="cuda"); x2 = torch.randn(R, c2, L, device="cuda") if c2 else None
     cout = net.specs[pre + ".block1.proj.weight"][0]
     for save in (True, False):
