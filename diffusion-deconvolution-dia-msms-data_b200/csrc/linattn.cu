@@ -164,7 +164,9 @@ __device__ __forceinline__ void take_x(const float* src, float (&v)[C]) {
 // and column xnT_s[0..CP)[j]; invalid positions (all-zero inputs) give zeros.
 // TROWS = rows of the transposed tile that are written: CP, or C when the caller lets the (never consumed) padding
 // columns of the B operand alias whatever follows the tile in shared memory.
-template <int C, int TROWS = TC<C>::CP>
+// ONES (C = 4 only): columns 4 and 5 of the [pos][8] row hold 1.0, so that per-channel constants ride in the spare
+// k-slots of the position x channel MMAs (constant = hi + lo split over the two slots).
+template <int C, int TROWS = TC<C>::CP, bool ONES = false>
 __device__ __forceinline__ void stage_xn(const float (&xin)[C], const float* __restrict__ g, float* xn_s, float* xnT_s,
                                          float* inv_s) {
   using T = TC<C>;
@@ -176,7 +178,8 @@ __device__ __forceinline__ void stage_xn(const float (&xin)[C], const float* __r
   const float inv = 1.f / fmaxf(sqrtf(s2), 1e-12f);
   const float sc = inv * sqrtf((float)C);
 #pragma unroll
-  for (int c = 0; c < T::CP; ++c) v[c] = (c < C) ? __uint_as_float(rtf(xin[c < C ? c : 0] * sc * __ldg(g + (c < C ? c : 0)))) : 0.f;
+  for (int c = 0; c < T::CP; ++c)
+    v[c] = (c < C) ? __uint_as_float(rtf(xin[c < C ? c : 0] * sc * __ldg(g + (c < C ? c : 0)))) : ((ONES && c < C + 2) ? 1.f : 0.f);
   if (xn_s) {
     float4* row = reinterpret_cast<float4*>(xn_s + j * T::XS);
 #pragma unroll
@@ -906,6 +909,9 @@ __global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la
   const float sqrtC = sqrtf((float)C);
   float* scrK = scr + h * 16 * RS;
 
+  // C = 4: log2e is folded into Wk, and the per-channel constants (softmax offset, -sd) into the spare k-slots of the
+  // xn operand, so exp2 / the softmax backward take the MMA outputs as they come
+  constexpr bool kFold = (C == 4);
   uint32_t bwk[4][T::KC][2], bh[4][T::KC][2], bkT[4][T::CT][2], bhT[4][T::CT][2];
   float cn[4][2], cd[4][2];
 #pragma unroll
@@ -915,8 +921,17 @@ __global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int c = 8 * ks + 2 * t + i, d = h * 32 + 8 * dt + g;
-        bwk[dt][ks][i] = f2tf(c < C ? a.wqkv[(size_t)(kHD + d) * C + c] : 0.f);
+        bwk[dt][ks][i] = f2tf(c < C ? a.wqkv[(size_t)(kHD + d) * C + c] * (kFold ? kLog2e : 1.f) : 0.f);
         bh[dt][ks][i] = f2tf(a.hmat[((size_t)r * kHD + d) * T::CP + c]);               // B[k = c][n = d] = H[d][c]
+        if (kFold && (c == C || c == C + 1)) {
+          // spare k-slots (the A rows carry 1.0 there): the softmax constant and -sd of channel d, split hi + lo
+          const size_t jd = (size_t)r * kHD + d;
+          const float cnd = kTfBias - (a.msm[jd * T::PS] * kLog2e + log2f(a.msm[jd * T::PS + 1]));
+          const float sdd = -a.sd[jd];
+          const float cn_hi = __uint_as_float(f2tf(cnd)), sd_hi = __uint_as_float(f2tf(sdd));
+          bwk[dt][ks][i] = (c == C) ? __float_as_uint(cn_hi) : f2tf(cnd - cn_hi);
+          bh[dt][ks][i] = (c == C) ? __float_as_uint(sd_hi) : f2tf(sdd - sd_hi);
+        }
       }
 #pragma unroll
     for (int ct = 0; ct < T::CT; ++ct)
@@ -931,8 +946,8 @@ __global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la
       const size_t jd = (size_t)r * kHD + h * 32 + 8 * dt + 2 * t + i;
       // softmax_L(k) = 2^(k log2e + cn); the + kTfBias pre-scales ks (and d k_raw = ks (..)) by (1 + 2^-11) so that the
       // MMA's operand truncation is unbiased without explicit rounding
-      cn[dt][i] = kTfBias - (a.msm[jd * T::PS] * kLog2e + log2f(a.msm[jd * T::PS + 1]));
-      cd[dt][i] = a.sd[jd];
+      cn[dt][i] = kFold ? 0.f : kTfBias - (a.msm[jd * T::PS] * kLog2e + log2f(a.msm[jd * T::PS + 1]));
+      cd[dt][i] = kFold ? 0.f : a.sd[jd];
     }
   }
   float dwk[2][T::CT][4];
@@ -957,7 +972,7 @@ __global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la
       cp_async_wait0();
       take_x<C>(pf_s + slot * C * SP, xv);
     }
-    stage_xn<C, C>(xv, a.g_pre, xn_s, xnT_s, inv_s);
+    stage_xn<C, C, (C == 4)>(xv, a.g_pre, xn_s, xnT_s, inv_s);
     if (!kAsync) {
 #pragma unroll
       for (int c = 0; c < C; ++c) xcur[c] = xv[c];
@@ -985,8 +1000,13 @@ __global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la
           mma_kc<T::KC>(dks[dt], ax, bh[dt]);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            kk[dt][i] = fexp2(fmaf(kk[dt][i], kLog2e, cn[dt][i & 1]));   // softmax_L(k)
-            dks[dt][i] = kk[dt][i] * (dks[dt][i] - cd[dt][i & 1]);       // d k_raw
+            if (kFold) {
+              kk[dt][i] = fexp2(kk[dt][i]);                                // softmax_L(k)
+              dks[dt][i] = kk[dt][i] * dks[dt][i];                         // d k_raw
+            } else {
+              kk[dt][i] = fexp2(fmaf(kk[dt][i], kLog2e, cn[dt][i & 1]));
+              dks[dt][i] = kk[dt][i] * (dks[dt][i] - cd[dt][i & 1]);
+            }
           }
         }
       }
