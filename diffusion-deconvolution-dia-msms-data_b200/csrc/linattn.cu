@@ -304,6 +304,76 @@ __device__ __forceinline__ void round_tile(const float (&v)[4][4], uint32_t (&o)
     for (int i = 0; i < 4; ++i) o[dt][i] = rtf(v[dt][i]);
 }
 
+// "Natural" A-operand layout of a normalised input sub-tile: per slab of 16 positions a block of CP channel rows of
+// AROW floats, position p of the slab at column 2 (p & 7) + (p >> 3).  The fragment registers (a0, a1) = rows g / g+8 of
+// k-slot t and (a2, a3) of k-slot t+4 are then two 64-bit loads that land in HMMA operand order (the [pos][c] layout
+// needs a 4-register permutation per fragment, which ptxas materialises as ~14 moves per slab); k-slot t <-> channel
+// 2t, t+4 <-> 2t+1 as everywhere; AROW = 20 and the slab stride = 16 (mod 32) keep loads and stores conflict-free.
+constexpr int AROW = 20;
+template <int C>
+struct TA {
+  static constexpr int SLAB = TC<C>::CP * AROW + 16;    // floats per slab block
+  static constexpr int SIZE = (SP / 16) * SLAB;
+};
+template <int C>
+__device__ __forceinline__ void stage_xn_nat(const float (&xin)[C], const float* __restrict__ g, float* xa_s) {
+  using T = TC<C>;
+  const int j = threadIdx.x;
+  float s2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) s2 = fmaf(xin[c], xin[c], s2);
+  const float sc = sqrtf((float)C) / fmaxf(sqrtf(s2), 1e-12f);
+  float* col = xa_s + (j >> 4) * TA<C>::SLAB + 2 * (j & 7) + ((j >> 3) & 1);
+#pragma unroll
+  for (int c = 0; c < T::CP; ++c)
+    col[c * AROW] = (c < C) ? __uint_as_float(rtf(xin[c < C ? c : 0] * sc * __ldg(g + (c < C ? c : 0)))) : 0.f;
+}
+template <int C>
+__device__ __forceinline__ void load_ax_nat(const float* xa_s, int s, int g, int t, uint32_t (&ax)[TC<C>::KC][4]) {
+#pragma unroll
+  for (int ks = 0; ks < TC<C>::KC; ++ks) {
+    const float* p = xa_s + s * TA<C>::SLAB + (8 * ks + 2 * t) * AROW + 2 * g;
+    const float2 v01 = *reinterpret_cast<const float2*>(p), v23 = *reinterpret_cast<const float2*>(p + AROW);
+    ax[ks][0] = __float_as_uint(v01.x); ax[ks][1] = __float_as_uint(v01.y);
+    ax[ks][2] = __float_as_uint(v23.x); ax[ks][3] = __float_as_uint(v23.y);
+  }
+}
+// softmax over the 32 columns of rows g and g+8 times `scale`, delivered as the A operand of the next MMA:
+// A[dt] = (q[dt][0], q[dt][2], q[dt][1], q[dt][3]).  After the exponentials the packed arithmetic pairs the two ROWS
+// (c0, c2) / (c1, c3), so the results are born in operand order and the row sums come out packed.
+__device__ __forceinline__ void softmax_rows_A(const float (&q)[4][4], float scale, uint32_t (&A)[4][4]) {
+  const unsigned long long l2e = pk2(kLog2e, kLog2e);
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int dt = 0; dt < 4; ++dt) {
+    mx0 = fmaxf(mx0, fmaxf(q[dt][0], q[dt][1]));
+    mx1 = fmaxf(mx1, fmaxf(q[dt][2], q[dt][3]));
+  }
+  const float nm0 = -quad_max(mx0) * kLog2e, nm1 = -quad_max(mx1) * kLog2e;
+  const unsigned long long n0 = pk2(nm0, nm0), n1 = pk2(nm1, nm1);
+  unsigned long long e02[4], e13[4], sm = pk2(0.f, 0.f);
+#pragma unroll
+  for (int dt = 0; dt < 4; ++dt) {
+    float a0, a1, a2, a3;
+    upk2(fma2(pk2(q[dt][0], q[dt][1]), l2e, n0), a0, a1);
+    upk2(fma2(pk2(q[dt][2], q[dt][3]), l2e, n1), a2, a3);
+    e02[dt] = pk2(fexp2(a0), fexp2(a2));
+    e13[dt] = pk2(fexp2(a1), fexp2(a3));
+    sm = add2(add2(sm, e02[dt]), e13[dt]);
+  }
+  float s0, s1;
+  upk2(sm, s0, s1);
+  const unsigned long long f = pk2(__fdividef(scale, quad_sum(s0)), __fdividef(scale, quad_sum(s1)));
+#pragma unroll
+  for (int dt = 0; dt < 4; ++dt) {
+    float x0, x1;
+    upk2(mul2(e02[dt], f), x0, x1);
+    A[dt][0] = __float_as_uint(x0); A[dt][1] = __float_as_uint(x1);
+    upk2(mul2(e13[dt], f), x0, x1);
+    A[dt][2] = __float_as_uint(x0); A[dt][3] = __float_as_uint(x1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------- forward: stats
 // K^T = Wk_h X^T as (32 channels x 16 positions) accumulator tiles; softmax over positions is a row-wise online
 // softmax with a lazy rescale; M[d][c] += P[d][n] Xn[n][c] re-uses the K^T accumulators as the A operand.
@@ -482,8 +552,8 @@ template <int C>
 __global__ void __launch_bounds__(128) la_out_kernel(LAArgs a) {
   using T = TC<C>;
   extern __shared__ float4 dyn_smem4[];
-  float* xn_s = reinterpret_cast<float*>(dyn_smem4);  // SP * XS
-  float* yp_s = xn_s + SP * T::XS;                    // 4 * SP * YS
+  float* xn_s = reinterpret_cast<float*>(dyn_smem4);  // TA<C>::SIZE: natural A-operand layout
+  float* yp_s = xn_s + TA<C>::SIZE;                   // 4 * SP * YS
   const int lane = threadIdx.x & 31, h = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int r = blockIdx.y;
   const int n_begin = blockIdx.x * a.chunk, n_end = min(a.L, n_begin + a.chunk);
@@ -512,7 +582,7 @@ __global__ void __launch_bounds__(128) la_out_kernel(LAArgs a) {
   float xv[C], xcur[C];
   load_x<C>(a.x, r, a.L, n_begin, n_end, xv);
   for (int n0 = n_begin; n0 < n_end; n0 += SP) {
-    stage_xn<C>(xv, a.g_pre, xn_s, nullptr, nullptr);
+    stage_xn_nat<C>(xv, a.g_pre, xn_s);
 #pragma unroll
     for (int c = 0; c < C; ++c) xcur[c] = xv[c];   // residual input of this sub-tile's epilogue
     __syncthreads();
@@ -520,20 +590,18 @@ __global__ void __launch_bounds__(128) la_out_kernel(LAArgs a) {
     const int nslab = min(SP / 16, (n_end - n0 + 15) / 16);
     for (int s = 0; s < nslab; ++s) {
       uint32_t ax[T::KC][4];
-      load_ax<C>(xn_s, s, g, t, ax);
+      load_ax_nat<C>(xn_s, s, g, t, ax);
       float q[4][4];
 #pragma unroll
       for (int dt = 0; dt < 4; ++dt) mma_kc<T::KC>(q[dt], ax, bq[dt]);
-      softmax_rows(q, scale * kTfBiasMul);   // q is only an MMA operand here: pre-bias against the truncation
+      uint32_t qa[4][4];
+      softmax_rows_A(q, scale * kTfBiasMul, qa);   // q is only an MMA operand here: pre-bias against the truncation
       float y[T::CT][4];
 #pragma unroll
       for (int ct = 0; ct < T::CT; ++ct) {
-        mma8_z(y[ct], __float_as_uint(q[0][0]), __float_as_uint(q[0][2]), __float_as_uint(q[0][1]), __float_as_uint(q[0][3]),
-               bg[0][ct][0], bg[0][ct][1]);
+        mma8_z(y[ct], qa[0][0], qa[0][1], qa[0][2], qa[0][3], bg[0][ct][0], bg[0][ct][1]);
 #pragma unroll
-        for (int kd = 1; kd < 4; ++kd)
-          mma8(y[ct], __float_as_uint(q[kd][0]), __float_as_uint(q[kd][2]), __float_as_uint(q[kd][1]), __float_as_uint(q[kd][3]),
-               bg[kd][ct][0], bg[kd][ct][1]);
+        for (int kd = 1; kd < 4; ++kd) mma8(y[ct], qa[kd][0], qa[kd][1], qa[kd][2], qa[kd][3], bg[kd][ct][0], bg[kd][ct][1]);
       }
 #pragma unroll
       for (int ct = 0; ct < T::CT; ++ct)
@@ -1107,7 +1175,7 @@ static int la_fwd(const LAArgs& a, cudaStream_t st) {
   DQ_LAUNCH_CHECK();
   la_combine_kernel<C><<<(unsigned)a.R, 128, 0, st>>>(a);
   DQ_LAUNCH_CHECK();
-  size_t smem = sizeof(float) * (SP * T::XS + 4 * SP * T::YS);
+  size_t smem = sizeof(float) * (TA<C>::SIZE + 4 * SP * T::YS);
   cudaFuncSetAttribute(la_out_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   la_out_kernel<C><<<grid, 128, smem, st>>>(a);
   DQ_LAUNCH_CHECK();
