@@ -166,7 +166,8 @@ __device__ __forceinline__ void take_x(const float* src, float (&v)[C]) {
 // columns of the B operand alias whatever follows the tile in shared memory.
 // ONES (C = 4 only): columns 4 and 5 of the [pos][8] row hold 1.0, so that per-channel constants ride in the spare
 // k-slots of the position x channel MMAs (constant = hi + lo split over the two slots).
-template <int C, int TROWS = TC<C>::CP, bool ONES = false>
+// NAT: xn_s is in the natural A-operand layout (TA<C>, see below) instead of [pos][XS] rows.
+template <int C, int TROWS = TC<C>::CP, bool ONES = false, bool NAT = false>
 __device__ __forceinline__ void stage_xn(const float (&xin)[C], const float* __restrict__ g, float* xn_s, float* xnT_s,
                                          float* inv_s) {
   using T = TC<C>;
@@ -181,9 +182,15 @@ __device__ __forceinline__ void stage_xn(const float (&xin)[C], const float* __r
   for (int c = 0; c < T::CP; ++c)
     v[c] = (c < C) ? __uint_as_float(rtf(xin[c < C ? c : 0] * sc * __ldg(g + (c < C ? c : 0)))) : ((ONES && c < C + 2) ? 1.f : 0.f);
   if (xn_s) {
-    float4* row = reinterpret_cast<float4*>(xn_s + j * T::XS);
+    if (NAT) {
+      float* col = xn_s + (j >> 4) * (T::CP * 20) + 2 * (j & 7) + ((j >> 3) & 1);
 #pragma unroll
-    for (int c4 = 0; c4 < T::CP / 4; ++c4) row[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+      for (int c = 0; c < T::CP; ++c) col[c * 20] = v[c];
+    } else {
+      float4* row = reinterpret_cast<float4*>(xn_s + j * T::XS);
+#pragma unroll
+      for (int c4 = 0; c4 < T::CP / 4; ++c4) row[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+    }
   }
   if (xnT_s) {
 #pragma unroll
@@ -308,11 +315,12 @@ __device__ __forceinline__ void round_tile(const float (&v)[4][4], uint32_t (&o)
 // AROW floats, position p of the slab at column 2 (p & 7) + (p >> 3).  The fragment registers (a0, a1) = rows g / g+8 of
 // k-slot t and (a2, a3) of k-slot t+4 are then two 64-bit loads that land in HMMA operand order (the [pos][c] layout
 // needs a 4-register permutation per fragment, which ptxas materialises as ~14 moves per slab); k-slot t <-> channel
-// 2t, t+4 <-> 2t+1 as everywhere; AROW = 20 and the slab stride = 16 (mod 32) keep loads and stores conflict-free.
-constexpr int AROW = 20;
+// 2t, t+4 <-> 2t+1 as everywhere; AROW = 20 keeps the fragment loads conflict-free (the staging stores, once per
+// sub-tile, are 2-way conflicted).
+constexpr int AROW = 20;   // (stage_xn's NAT branch spells the same numbers out: it is defined before this point)
 template <int C>
 struct TA {
-  static constexpr int SLAB = TC<C>::CP * AROW + 16;    // floats per slab block
+  static constexpr int SLAB = TC<C>::CP * AROW;         // floats per slab block
   static constexpr int SIZE = (SP / 16) * SLAB;
 };
 template <int C>
@@ -647,11 +655,11 @@ __global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la
   // C = 4: ONE [pos][8] tile with xn and dy interleaved (xn0, dy0, xn1, dy1, ..): a single A fragment then carries xn
   // in k = 0..3 and dy in k = 4..7, and the two B operands (Wq^T | 0) and (0 | G) need one register each
   constexpr bool kMerged = (C == 4);
-  float* xn_s = reinterpret_cast<float*>(dyn_smem4);   // SP * XS
-  float* dy_s = xn_s + (kMerged ? 0 : SP * T::XS);     // SP * XS (merged: same tile)
+  float* xn_s = reinterpret_cast<float*>(dyn_smem4);   // TA<C>::SIZE (natural A-operand layout)
+  float* dy_s = xn_s + (kMerged ? 0 : TA<C>::SIZE);    // TA<C>::SIZE (merged: same tile)
   // transposed tiles hold only the C real channel rows: rows C..CP-1 of a B fragment (n = channel) alias the next
   // array; those accumulator columns are never stored
-  float* xnT_s = dy_s + SP * T::XS;                    // C * XT
+  float* xnT_s = dy_s + TA<C>::SIZE;                   // C * XT
   float* dyT_s = xnT_s + C * XT;                       // C * XT
   float* yp_s = dyT_s + C * XT;                        // 4 * SP * YS   per-head d xn_q
   float* scr = yp_s + 4 * SP * T::YS;                  // 4 warps * 2 tiles * 16 * RS
@@ -719,7 +727,7 @@ __global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la
       take_x<C>(pf_s + C * SP, yv);
       take_x<C>(pf_s + 2 * C * SP, drv);
     }
-    stage_xn<C, C>(xv, a.g_pre, kMerged ? nullptr : xn_s, xnT_s, nullptr);
+    stage_xn<C, C, false, true>(xv, a.g_pre, kMerged ? nullptr : xn_s, xnT_s, nullptr);
     {  // d y = RMSNorm_out backward of d res, thread j = position
       const int j = threadIdx.x, n = n0 + j;
       const bool ok = n < n_end;
@@ -754,13 +762,16 @@ __global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la
         dv[c] = __uint_as_float(rtf(d));
         if (c < C) dyT_s[c * XT + j] = dv[c];
       }
-      float4* row = reinterpret_cast<float4*>(dy_s + j * T::XS);
-      if (kMerged) {  // xn comes back from its own column of the transposed tile (written by this thread)
-        row[0] = make_float4(xnT_s[0 * XT + j], dv[0], xnT_s[1 * XT + j], dv[1]);
-        row[1] = make_float4(xnT_s[2 * XT + j], dv[2], xnT_s[(C > 3 ? 3 : 0) * XT + j], dv[3]);
+      float* col = dy_s + (j >> 4) * TA<C>::SLAB + 2 * (j & 7) + ((j >> 3) & 1);
+      if (kMerged) {  // rows (xn0, dy0, xn1, dy1, ..); xn comes back from its own column of the transposed tile
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          col[(2 * c) * AROW] = xnT_s[c * XT + j];
+          col[(2 * c + 1) * AROW] = dv[c];
+        }
       } else {
 #pragma unroll
-        for (int c4 = 0; c4 < T::CP / 4; ++c4) row[c4] = make_float4(dv[4 * c4], dv[4 * c4 + 1], dv[4 * c4 + 2], dv[4 * c4 + 3]);
+        for (int c = 0; c < T::CP; ++c) col[c * AROW] = dv[c];
       }
     }
     __syncthreads();
@@ -781,7 +792,7 @@ __global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la
       float qs[4][4], dqs[4][4];
       {
         uint32_t ax[T::KC][4];
-        load_ax<C>(xn_s, s, g, t, ax);
+        load_ax_nat<C>(xn_s, s, g, t, ax);
         if (kMerged) {
 #pragma unroll
           for (int dt = 0; dt < 4; ++dt) {
@@ -791,7 +802,7 @@ __global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la
         } else {
 #pragma unroll
           for (int dt = 0; dt < 4; ++dt) mma_kc<T::KC>(qs[dt], ax, bq[dt]);
-          load_ax<C>(dy_s, s, g, t, ax);
+          load_ax_nat<C>(dy_s, s, g, t, ax);
 #pragma unroll
           for (int dt = 0; dt < 4; ++dt) mma_kc<T::KC>(dqs[dt], ax, bgA[dt]);
         }
@@ -963,8 +974,8 @@ template <int C>
 __global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la_bwd_kv_kernel(LAArgs a) {
   using T = TC<C>;
   extern __shared__ float4 dyn_smem4[];
-  float* xn_s = reinterpret_cast<float*>(dyn_smem4);   // SP * XS
-  float* xnT_s = xn_s + SP * T::XS;                    // C * XT (see la_bwd_q_kernel)
+  float* xn_s = reinterpret_cast<float*>(dyn_smem4);   // TA<C>::SIZE (natural A-operand layout)
+  float* xnT_s = xn_s + TA<C>::SIZE;                   // C * XT (see la_bwd_q_kernel)
   float* yp_s = xnT_s + C * XT;                        // 4 * SP * YS
   float* scr = yp_s + 4 * SP * T::YS;                  // 4 warps * 16 * RS
   float* inv_s = scr + 4 * 16 * RS;                    // SP
@@ -1040,7 +1051,7 @@ __global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la
       cp_async_wait0();
       take_x<C>(pf_s + slot * C * SP, xv);
     }
-    stage_xn<C, C, (C == 4)>(xv, a.g_pre, xn_s, xnT_s, inv_s);
+    stage_xn<C, C, (C == 4), true>(xv, a.g_pre, xn_s, xnT_s, inv_s);
     if (!kAsync) {
 #pragma unroll
       for (int c = 0; c < C; ++c) xcur[c] = xv[c];
@@ -1061,7 +1072,7 @@ __global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la
       float kk[4][4], dks[4][4];
       {
         uint32_t ax[T::KC][4];
-        load_ax<C>(xn_s, s, g, t, ax);
+        load_ax_nat<C>(xn_s, s, g, t, ax);
 #pragma unroll
         for (int dt = 0; dt < 4; ++dt) {
           mma_kc<T::KC>(kk[dt], ax, bwk[dt]);
@@ -1187,7 +1198,7 @@ static int la_bwd(const LAArgs& a, cudaStream_t st) {
   using T = TC<C>;
   dim3 grid((unsigned)a.nchunk, (unsigned)a.R);
   {
-    size_t smem = sizeof(float) * ((C == 4 ? 1 : 2) * SP * T::XS + 2 * C * XT + 4 * SP * T::YS + 4 * 2 * 16 * RS + 2 * C +
+    size_t smem = sizeof(float) * ((C == 4 ? 1 : 2) * TA<C>::SIZE + 2 * C * XT + 4 * SP * T::YS + 4 * 2 * 16 * RS + 2 * C +
                                    (C == 4 ? 3 * C * SP : 0));
     cudaFuncSetAttribute(la_bwd_q_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     la_bwd_q_kernel<C><<<grid, 128, smem, st>>>(a);
@@ -1201,7 +1212,7 @@ static int la_bwd(const LAArgs& a, cudaStream_t st) {
     DQ_LAUNCH_CHECK();
   }
   {
-    size_t smem = sizeof(float) * (SP * T::XS + C * XT + 4 * SP * T::YS + 4 * 16 * RS + SP + C + (C == 4 ? 4 * C * SP : 0));
+    size_t smem = sizeof(float) * (TA<C>::SIZE + C * XT + 4 * SP * T::YS + 4 * 16 * RS + SP + C + (C == 4 ? 4 * C * SP : 0));
     cudaFuncSetAttribute(la_bwd_kv_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     la_bwd_kv_kernel<C><<<grid, 128, smem, st>>>(a);
     DQ_LAUNCH_CHECK();
