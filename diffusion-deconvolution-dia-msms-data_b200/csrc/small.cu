@@ -203,6 +203,102 @@ __global__ void down_w_kernel(float* __restrict__ w4, float* __restrict__ w3, in
   }
 }
 static inline unsigned ew_grid(long n) { long g = (n + 255) / 256; return (unsigned)(g > 148L * 16 ? 148L * 16 : g); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Backward of init_conv = Conv1d(2 -> COUT, k7, pad 3) over cat(ConditionalScaleShift(cond), x) (unet1d.py:1107-1117,
+// 677-678) in ONE pass over (d, cond, x), without the data gradient ever existing.  Per sample s the pass produces the
+// RAW correlations  G_s[co][ci][k] = sum_{rows of s, p} d[co][p] in_ci[p + k - 3]  (cond NOT scaled / shifted),
+// D_s[co] = sum d[co][p] and the edge sums E_s[co][k] = sum of d[co][p] over the positions whose tap k falls outside the
+// row.  Everything else is algebra on those 18 COUT numbers (initconv_bwd_finalize_kernel):
+//   dW[co][0][k] += (1 + scale_s) G_s[co][0][k] + shift_s (D_s[co] - E_s[co][k]);   dW[co][1][k] += G_s[co][1][k]
+//   db[co] += D_s[co];   d scale_s = sum_{co,k} W[co][0][k] G_s[co][0][k];   d shift_s = sum W[co][0][k] (D_s - E_s)
+// Scratch record per sample and group of 4 output channels: G (4*2*7) | D (4) | E (4*7) = 88 floats.
+constexpr int IC_REC = 88;
+__global__ void __launch_bounds__(128) initconv_bwd_kernel(const float* __restrict__ d, const float* __restrict__ cond,
+                                                           const float* __restrict__ x, float* __restrict__ scratch,
+                                                           int cout, int L, int chunk, int rows_per_sample) {
+  __shared__ float red[4 * 60];
+  const int r = blockIdx.y, cg = blockIdx.z;
+  const int n_begin = blockIdx.x * chunk, n_end = min(L, n_begin + chunk);
+  const float* dr = d + ((size_t)r * cout + 4 * cg) * L;
+  const float* in[2] = {cond + (size_t)r * L, x + (size_t)r * L};
+  float acc[60];
+#pragma unroll
+  for (int i = 0; i < 60; ++i) acc[i] = 0.f;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = n_begin + 4 * threadIdx.x; p < n_end; p += 4 * 128) {
+    float dv[4][4];
+#pragma unroll
+    for (int co = 0; co < 4; ++co) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(dr + (size_t)co * L + p));
+      dv[co][0] = v.x; dv[co][1] = v.y; dv[co][2] = v.z; dv[co][3] = v.w;
+      acc[56 + co] += (v.x + v.y) + (v.z + v.w);
+    }
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci) {
+      const float4 a = p >= 4 ? __ldg(reinterpret_cast<const float4*>(in[ci] + p - 4)) : z4;
+      const float4 b = __ldg(reinterpret_cast<const float4*>(in[ci] + p));
+      const float4 c = p + 4 < L ? __ldg(reinterpret_cast<const float4*>(in[ci] + p + 4)) : z4;
+      const float w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};   // positions p - 4 .. p + 7
+#pragma unroll
+      for (int co = 0; co < 4; ++co)
+#pragma unroll
+        for (int k = 0; k < 7; ++k)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[(co * 2 + ci) * 7 + k] = fmaf(dv[co][i], w[i + k + 1], acc[(co * 2 + ci) * 7 + k]);
+    }
+    // taps that leave the row: k < 3 at positions p' < 3 - k, k > 3 at positions p' > L - 1 - (k - 3)
+    if (p == 0 || p + 4 >= L) {
+      float* e = scratch + ((size_t)(r / rows_per_sample) * gridDim.z + cg) * IC_REC + 60;
+#pragma unroll
+      for (int co = 0; co < 4; ++co) {
+        if (p == 0) {
+          atomicAdd(e + co * 7 + 0, dv[co][0] + dv[co][1] + dv[co][2]);
+          atomicAdd(e + co * 7 + 1, dv[co][0] + dv[co][1]);
+          atomicAdd(e + co * 7 + 2, dv[co][0]);
+        }
+        if (p + 4 >= L) {
+          atomicAdd(e + co * 7 + 4, dv[co][3]);
+          atomicAdd(e + co * 7 + 5, dv[co][3] + dv[co][2]);
+          atomicAdd(e + co * 7 + 6, dv[co][3] + dv[co][2] + dv[co][1]);
+        }
+      }
+    }
+  }
+  const float tot = block_reduce_vec<60>(acc, red);
+  if (threadIdx.x < 60) atomicAdd(scratch + ((size_t)(r / rows_per_sample) * gridDim.z + cg) * IC_REC + threadIdx.x, tot);
+}
+
+__global__ void __launch_bounds__(64) initconv_bwd_finalize_kernel(const float* __restrict__ scratch, const float* __restrict__ w,
+                                                                   const float* __restrict__ ss, int ss_stride, float* dw,
+                                                                   float* db, float* dss, int cout) {
+  __shared__ float red[2 * 2];
+  const int s = blockIdx.x, cg = blockIdx.y, i = threadIdx.x;
+  const float* rec = scratch + ((size_t)s * gridDim.y + cg) * IC_REC;
+  const float scale = ss ? ss[(size_t)s * ss_stride] + 1.f : 1.f, shift = ss ? ss[(size_t)s * ss_stride + 1] : 0.f;
+  float v[2] = {0.f, 0.f};
+  if (i < 56) {
+    const int k = i % 7, ci = (i / 7) % 2, co = 4 * cg + i / 14;
+    const float g = rec[i];
+    if (ci == 0) {
+      const float sv = rec[56 + i / 14] - rec[60 + (i / 14) * 7 + k];   // D - E
+      const float wv = w[((size_t)co * 2 + 0) * 7 + k];
+      atomicAdd(dw + ((size_t)co * 2 + 0) * 7 + k, scale * g + shift * sv);
+      v[0] = wv * g;
+      v[1] = wv * sv;
+    } else {
+      atomicAdd(dw + ((size_t)co * 2 + 1) * 7 + k, g);
+    }
+  } else if (i < 60) {
+    if (db) atomicAdd(db + 4 * cg + (i - 56), rec[i]);
+  }
+  const float tot = block_reduce_vec<2>(v, red);
+  if (ss && dss) {
+    if (i == 0) atomicAdd(dss + (size_t)s * ss_stride, tot);
+    if (i == 1) atomicAdd(dss + (size_t)s * ss_stride + 1, tot);
+  }
+}
+
 }  // namespace dq
 
 DQ_API int dq_upsample2x(const float* x, float* y, long n, void* stream) {
@@ -236,6 +332,27 @@ DQ_API int dq_d2s(const float* d, float* dx, int R, int C, int L, int acc, void*
 DQ_API int dq_down_w(float* w4, float* w3, int co, int ci, int dir, void* stream) {
   if (co * ci <= 0) return 0;
   dq::down_w_kernel<<<(unsigned)((co * ci + 127) / 128), 128, 0, (cudaStream_t)stream>>>(w4, w3, co, ci, dir);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+
+// Backward of init_conv (Conv1d(2 -> cout, k7, pad 3) over cat(cond * (scale + 1) + shift, x)): dW, db and the
+// per-sample d scale / d shift of the ConditionalScaleShift in one pass, no data gradient tensor.  scratch: (b, cout / 4,
+// 88) floats, ZEROED by the caller.  ss / dss: scale at [s * ss_stride], shift at [s * ss_stride + 1].  Returns 1 (nothing
+// launched) unless cout % 4 == 0, L % 4 == 0 and the rows are 16-byte aligned.
+DQ_API int dq_initconv_bwd(const float* d, const float* cond, const float* x, const float* ss, int ss_stride, const float* w,
+                           float* dw, float* db, float* dss, float* scratch, int cout, int R, int L, int rows_per_sample,
+                           void* stream) {
+  if (R <= 0 || L <= 0) return 0;
+  if ((cout & 3) || (L & 3) || ((((size_t)d | (size_t)cond | (size_t)x) & 15) != 0) || R % rows_per_sample) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nchunk = (L + 8191) / 8192;
+  const int chunk = ((L + nchunk - 1) / nchunk + 511) / 512 * 512;
+  dim3 grid((unsigned)((L + chunk - 1) / chunk), (unsigned)R, (unsigned)(cout / 4));
+  dq::initconv_bwd_kernel<<<grid, 128, 0, st>>>(d, cond, x, scratch, cout, L, chunk, rows_per_sample);
+  DQ_LAUNCH_CHECK();
+  dim3 g2((unsigned)(R / rows_per_sample), (unsigned)(cout / 4));
+  dq::initconv_bwd_finalize_kernel<<<g2, 64, 0, st>>>(scratch, w, ss, ss_stride, dw, db, dss, cout);
   DQ_LAUNCH_CHECK();
   return 0;
 }

@@ -28,6 +28,7 @@ _SIGS = {
     "dq_conv1d_bwd_weight": ("ppipipippiiiiiiiiis", 1),
     "dq_conv_bwd_fused": ("ppppiipipipppipippppiiiiis", 1),
     "dq_conv_bwd_fused_res": ("pppp" + "ii" + "pipi" + "ppp" + "pppp" + "pppp" + "iiii" + "s", 1),
+    "dq_initconv_bwd": ("pppp" + "i" + "ppppp" + "iiii" + "s", 2),
     "dq_resblock_fwd": ("pipippppipppppppppiiiis", 1),
     "dq_sample_dot": ("ppppilis", 1),
     "dq_upsample2x": ("ppls", 1),

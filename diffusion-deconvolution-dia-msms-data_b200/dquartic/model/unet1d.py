@@ -936,14 +936,23 @@ class UNet1d(nn.Module):
         # init conv: gradient of its output = down-path gradient + final-res-block skip gradient
         N.call("dq_add_inplace", dcur, dx0, dcur.numel())
         ico = self.ss_off["init_cond_proj.to_scale_shift.1"]
-        dxc = self._empty(R, 1, L)
-        # weight/bias gradient with the ConditionalScaleShift applied to source 1; data gradient only for channel 0
-        self._conv_bwd(dcur, S["ic"], S["x"], "init_conv.weight", "init_conv.bias", 7, 1, 3, 1, need_dx1=False,
-                       need_dx2=False, in_ss=ico, rps=rt)
-        N.call("dq_conv1d_bwd_data", dcur, self._w("init_conv.weight"), dxc, 1, 0, None, 1, 0, self.dim, 7, 1, 3, 1,
-               R, L, L)
-        N.call("dq_sample_dot", dxc, S["ic"], _off_ptr(self._dSS[:, ico:]), _off_ptr(self._dSS[:, ico + 1:]),
-               self.ss_total, rt * L, b)
+        # one pass over (d, cond, x): dW, db and the per-sample d scale / d shift of the ConditionalScaleShift from raw
+        # per-sample correlations (csrc/small.cu); the data gradient of the conditioning channel never exists
+        rc = 1
+        if S["ic"].shape[1] == 1 and S["x"].shape[1] == 1:
+            scratch = torch.zeros(b, max(1, self.dim // 4), 88, device=dcur.device, dtype=torch.float32)
+            rc = N.call("dq_initconv_bwd", dcur, S["ic"], S["x"], _off_ptr(self._SS[:, ico:]), self.ss_total,
+                        self._w("init_conv.weight"), self._gw("init_conv.weight"), self._gw("init_conv.bias"),
+                        _off_ptr(self._dSS[:, ico:]), scratch, self.dim, R, L, rt, allow=(1,))
+        if rc != 0:
+            dxc = self._empty(R, 1, L)
+            # weight/bias gradient with the ConditionalScaleShift applied to source 1; data gradient only for channel 0
+            self._conv_bwd(dcur, S["ic"], S["x"], "init_conv.weight", "init_conv.bias", 7, 1, 3, 1, need_dx1=False,
+                           need_dx2=False, in_ss=ico, rps=rt)
+            N.call("dq_conv1d_bwd_data", dcur, self._w("init_conv.weight"), dxc, 1, 0, None, 1, 0, self.dim, 7, 1, 3, 1,
+                   R, L, L)
+            N.call("dq_sample_dot", dxc, S["ic"], _off_ptr(self._dSS[:, ico:]), _off_ptr(self._dSS[:, ico + 1:]),
+                   self.ss_total, rt * L, b)
 
         # MS1 conditioning path
         da2 = self._empty(b, acd, rt)

@@ -83,6 +83,14 @@ int dq_fold2x(const float* d, float* dx, long n, int acc, void* stream);
 int dq_s2d(const float* x, float* y, int R, int C, int L, void* stream);
 int dq_d2s(const float* d, float* dx, int R, int C, int L, int acc, void* stream);
 int dq_down_w(float* w4, float* w3, int co, int ci, int dir, void* stream);
+/* Backward of init_conv = Conv1d(2 -> cout, k7, pad 3) over cat(ConditionalScaleShift(cond), x) (unet1d.py:1107-1117,
+ * 677-678) in one pass: dW, db and the per-sample d scale / d shift (dss[s*ss_stride], [.. + 1]) from raw per-sample
+ * correlations; no data gradient tensor.  scratch: (R / rows_per_sample, cout / 4, 88) floats zeroed by the caller.
+ * Returns 1 (nothing launched) unless cout % 4 == 0, L % 4 == 0 and 16-byte aligned rows: then use
+ * dq_conv1d_bwd_weight + dq_conv1d_bwd_data + dq_sample_dot. */
+int dq_initconv_bwd(const float* d, const float* cond, const float* x, const float* ss, int ss_stride, const float* w,
+                    float* dw, float* db, float* dss, float* scratch, int cout, int R, int L, int rows_per_sample,
+                    void* stream);
 /* gradient of ConditionalScaleShift (unet1d.py:677-678): per-sample sum d*c and sum d. */
 int dq_sample_dot(const float* d, const float* c, float* dscale, float* dshift, int out_stride, long n_per_sample,
                   int n_samples, void* stream);
