@@ -525,7 +525,9 @@ class UNet1d(nn.Module):
                                  g=pre + ".block2.norm.g", act=ACT_SILU, res=res, save_u=save, rps=rps)
         return out, (x1, x2, u1, h1, u2)
 
-    def _resnet_bwd(self, pre, saved, dout, rps, need_dx=True):
+    def _resnet_bwd(self, pre, saved, dout, rps, need_dx=True, dx_acc=None):
+        """`dx_acc` (identity-skip blocks only): a tensor of dx1's shape the input gradient is ACCUMULATED into (the
+        skip-connection gradient that would otherwise be added by a separate pass); it is returned as dx1."""
         x1, x2, u1, h1, u2 = saved
         dh1, _ = self._conv_bwd_fused(dout, u2, pre + ".block2.norm.g", None, ACT_SILU, h1, None,
                                       pre + ".block2.proj.weight", pre + ".block2.proj.bias", 3, rps=rps)
@@ -547,7 +549,8 @@ class UNet1d(nn.Module):
                 return dx1, dx2
         dx1, dx2 = self._conv_bwd_fused(dh1, u1, pre + ".block1.norm.g", self.ss_off[pre + ".mlp.1"], ACT_SILU, x1, x2,
                                         pre + ".block1.proj.weight", pre + ".block1.proj.bias", 3, need_dx1=need_dx,
-                                        need_dx2=need_dx, dadd=None if (has_res or not need_dx) else dout, rps=rps)
+                                        need_dx2=need_dx, dx1=None if has_res else dx_acc,
+                                        dadd=None if (has_res or not need_dx) else dout, rps=rps)
         if has_res:
             dx1, dx2 = self._conv_bwd_fused(dout, None, None, None, ACT_NONE, x1, x2, pre + ".res_conv.weight",
                                             pre + ".res_conv.bias", 1, need_dx1=need_dx, need_dx2=need_dx, dx1=dx1,
@@ -929,12 +932,16 @@ class UNet1d(nn.Module):
             else:
                 dc, _ = self._conv_bwd(dcur, c, None, pre + ".3.weight", pre + ".3.bias", 3, 1, 1, 1, dx1=dskip_c, rps=rt)
             db = self._la_bwd(pre + ".2", s2, dc)
-            da, _ = self._resnet_bwd(pre + ".1", s1, db, rt)
-            N.call("dq_add_inplace", da, dskip_a, da.numel())
-            dcur, _ = self._resnet_bwd(pre + ".0", s0, da, rt)
+            has_res = (pre + ".1.res_conv.weight") in self.specs
+            da, _ = self._resnet_bwd(pre + ".1", s1, db, rt, dx_acc=None if has_res else dskip_a)   # += skip gradient
+            if has_res:
+                N.call("dq_add_inplace", da, dskip_a, da.numel())
+            last = (i == 0) and (pre + ".0.res_conv.weight") not in self.specs
+            dcur, _ = self._resnet_bwd(pre + ".0", s0, da, rt, dx_acc=dx0 if last else None)
 
         # init conv: gradient of its output = down-path gradient + final-res-block skip gradient
-        N.call("dq_add_inplace", dcur, dx0, dcur.numel())
+        if "downs.0.0.res_conv.weight" in self.specs:   # otherwise dx0 was accumulated by the block backward above
+            N.call("dq_add_inplace", dcur, dx0, dcur.numel())
         ico = self.ss_off["init_cond_proj.to_scale_shift.1"]
         # one pass over (d, cond, x): dW, db and the per-sample d scale / d shift of the ConditionalScaleShift from raw
         # per-sample correlations (csrc/small.cu); the data gradient of the conditioning channel never exists
