@@ -12,6 +12,8 @@ b = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 rt, mz = 136, 40000
 dev = torch.device("cuda")
+torch.manual_seed(0)
+torch.cuda.manual_seed_all(0)
 t0 = time.time()
 net = UNet1d(dim=8, channels=1, dim_mults=(1, 2, 2, 3, 3, 4, 4), conditional=True, init_cond_channels=1,
              attn_cond_channels=1, downsample_dim=mz, device=dev)
