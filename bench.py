@@ -376,7 +376,10 @@ def dominant_kernel_roofline(torch, N, net, dev, n_samples=64):
     exp_floor_ms = lambda n_exp: n_exp * R * L / (148 * 16 * 1.965e9) * 1e3
     main = {"kernel": f"dq_linattn_bwd (la_bwd_q + la_bwd_combine + la_bwd_kv), level 0 (C=4, L=40000), {n_samples} samples",
             "bound": "tensor", "achieved": ach_b, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach_b / pk["tensor"],
-            "traffic": None, "ms_per_launch": ms_b, "peak_source": pk["src"],
+            # dram__bytes_read.sum + dram__bytes_write.sum of la_bwd_q + la_bwd_combine + la_bwd_kv at exactly this shape
+            # (C = 4, L = 40000, 64 samples), one `ncu --set full` capture: profiles/r1d_la_bwd64_ncu_full_summary.txt
+            "traffic": (11.232e9 if n_samples == 64 else None), "traffic_unit": "bytes per dq_linattn_bwd call",
+            "ms_per_launch": ms_b, "peak_source": pk["src"],
             "note": "algorithmic FLOPs = the reference's 32x32 per-head bmm's; the kernels factor them through the C "
                     "input channels (32xC products, ~1/4 of the MMA work at C=4, mma.sync TF32) and are bound by "
                     "MUFU.EX2 + instruction issue, not by the tensor pipe or HBM: MUFU floor "
