@@ -217,7 +217,10 @@ def main():
     ms2, ms1 = synth_pool(args.pool, RT, MZ, seed=1234)
     np.save(os.path.join(tmp, "ms2.npy"), ms2)
     np.save(os.path.join(tmp, "ms1.npy"), ms1)
-    ds = DIAMSDataset(ms2_file=os.path.join(tmp, "ms2.npy"), ms1_file=os.path.join(tmp, "ms1.npy"), normalize="minmax")
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):   # the dataset prints an "Info: Loaded .." line (as the reference does);
+        ds = DIAMSDataset(ms2_file=os.path.join(tmp, "ms2.npy"), ms1_file=os.path.join(tmp, "ms1.npy"), normalize="minmax")
+    # stdout carries the ONE JSON line only
     random.seed(1234 + rank)
     torch.manual_seed(1234 + rank)
 
