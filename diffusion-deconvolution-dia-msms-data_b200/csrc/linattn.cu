@@ -27,36 +27,12 @@
 // We use a fixed permutation of the k index inside every k8 block: slot t <-> actual k = 2t, slot t+4 <-> 2t+1.
 // Then (c0, c2, c1, c3) of an accumulator tile IS an A fragment and operands that come from memory are loaded
 // with the same permutation (one 64-bit load).
+#include <stdlib.h>
 #include "common.cuh"
+#include "linattn_args.cuh"
 
 namespace dq {
 
-struct LAArgs {
-  const float* x;      // (R, C, L) block input
-  const float* g_pre;  // (C) PreNorm gain
-  const float* wqkv;   // (384, C)
-  const float* wout;   // (C, 128)
-  const float* bout;   // (C)
-  const float* g_out;  // (C)
-  float* part;         // (R, nchunk, 128, 2+CP) forward partials [m, s, M[CP]]
-  float* msm;          // (R, 128, 2+CP)  [m, s, Ms[CP]]  saved for backward
-  float* gmat;         // (R, C, 128)     G[c'][h*32+d]    saved for backward
-  float* ypre;         // (R, C, L) to_out output before RMSNorm (saved for backward; may be null)
-  float* out;          // (R, C, L)
-  // backward
-  const float* dres;   // (R, C, L) gradient of the block output
-  float* dxnq;         // (R, C, L) scratch: q-path gradient w.r.t. the pre-normed input
-  float* dpart;        // (R, nchunk, 128, CP) partial Gq
-  float* hmat;         // (R, 128, CP)  H[h*32+d][c]
-  float* sd;           // (R, 128)      sum_e dctx*ctx
-  float* dx;           // (R, C, L)
-  float* dwqkv;        // (384, C) accumulated
-  float* dwout;        // (C, 128) accumulated
-  float* dbout;        // (C) accumulated
-  float* dg_out;       // (C) accumulated
-  float* dg_pre;       // (C) accumulated
-  int R, L, chunk, nchunk;
-};
 
 template <int C>
 struct TC {
@@ -1178,6 +1154,13 @@ __global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la
   if (threadIdx.x < C) atomicAdd(a.dg_pre + threadIdx.x, acc_s[threadIdx.x]);
 }
 
+// DQ_LA_TC=0 selects the mma.sync kernels of this file everywhere (cross-check / A-B timing); default: tcgen05 kernels
+static bool la_tc_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DQ_LA_TC"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 template <int C>
 static int la_fwd(const LAArgs& a, cudaStream_t st) {
   using T = TC<C>;
@@ -1197,7 +1180,13 @@ template <int C>
 static int la_bwd(const LAArgs& a, cudaStream_t st) {
   using T = TC<C>;
   dim3 grid((unsigned)a.nchunk, (unsigned)a.R);
-  {
+  bool q_done = false;
+  if (la_tc_enabled() && C <= 16) {   // tcgen05 / TMEM kernel (linattn_tc.cu)
+    const int rc = la_bwd_q_tc(a, C, st);
+    if (rc != 0) return rc;
+    q_done = true;
+  }
+  if (!q_done) {
     size_t smem = sizeof(float) * ((C == 4 ? 1 : 2) * TA<C>::SIZE + 2 * C * XT + 4 * SP * T::YS + 4 * 2 * 16 * RS + 2 * C +
                                    (C == 4 ? 3 * C * SP : 0));
     cudaFuncSetAttribute(la_bwd_q_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

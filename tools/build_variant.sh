@@ -7,7 +7,7 @@ name=$1; flags=$2; shift 2 || true
 files=${@:-linattn.cu}
 mkdir -p ../../build/ab/$name
 objs=""
-for f in conv.cu conv_fused.cu linattn.cu gemm_tcgen05.cu sched.cu small.cu mid.cu optim.cu data.cu; do
+for f in conv.cu conv_fused.cu linattn.cu linattn_tc.cu gemm_tcgen05.cu sched.cu small.cu mid.cu optim.cu data.cu; do
   if [[ " $files " == *" $f "* ]]; then
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden $flags -c $f -o ../../build/ab/$name/${f%.cu}.o
     objs="$objs ../../build/ab/$name/${f%.cu}.o"

@@ -415,6 +415,44 @@ __global__ void __launch_bounds__(128) tmem_bench_kernel(float* out, int iters, 
   if (warp == 0) tmem_dealloc(tm, 128);
 }
 
+
+// ------------------------------------------------------------------------------------------------ MMA issue rate
+// One CTA per SM; thread 0 issues `n` identical MMAs back to back, commits, waits.  mode 0: SS tf32 K-major N = nn, K = 8;
+// 1: TS tf32 (A in TMEM) N = nn, K = 8;  2: SS bf16 A MN-major N = nn, K = 16.  Reports cycles per MMA (clock64 on the SM).
+__global__ void __launch_bounds__(128) mma_rate_kernel(int n, int mode, int nn, int nacc, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // finite in every format
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc(smem_u32(&tslot), 512);
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tslot;
+  if (tid == 0) {
+    const uint32_t sa = smem_u32(smem), sb = sa + 32 * 1024;
+    const uint64_t da = umma_desc_ns(sa, 128, mode == 2 ? 2048 : 256), db = umma_desc_ns(sb, 128, mode == 2 ? 2048 : 256);
+    const uint32_t idesc = mode == 2 ? make_idesc(kBF16, 128, nn, 1, 0) : make_idesc(kTF32, 128, nn, 0, 0);
+    const long long t0 = clock64();
+    for (int i = 0; i < n; ++i) {
+      const uint32_t d = tm + (uint32_t)((i % nacc) * 32);   // nacc independent accumulators (N <= 32 when nacc > 1)
+      if (mode == 0) mma_ss_tf32(d, da, db, idesc, 1);
+      else if (mode == 1) mma_ts_tf32(d, tm + 256, db, idesc, 1);
+      else mma_ss_f16(d, da, db, idesc, 1);
+    }
+    umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) *cycles = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
 // ------------------------------------------------------------------------------------------------ host
 static float rnd_small(uint32_t& s, int range) { s = s * 1664525u + 1013904223u; return (float)((int)((s >> 16) % (2 * range + 1)) - range); }
 
@@ -517,6 +555,21 @@ int main(int argc, char** argv) {
       double bytes = (double)sms * occ * 128 * 64 * 4 * iters;
       printf("tmem %s %2d warps/SM: %.3f ms  %.1f B/clk/SM\n", mode ? "st" : "ld", occ * 4, ms, bytes / (ms * 1e-3) / (ghz * 1e9) / sms);
     }
+  }
+  {
+    long long* dc; CK(cudaMalloc(&dc, 8));
+    CK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    const char* nm[3] = {"SS tf32 K=8", "TS tf32 K=8", "SS bf16 MN-major K=16"};
+    for (int mode = 0; mode < 3; ++mode)
+      for (int nacc : {1, 2, 4, 8})
+        for (int nn : {16, 32, 128}) {
+          if (nacc > 1 && nn > 32) continue;
+          const int n = 2000;
+          mma_rate_kernel<<<sms, 128, 64 * 1024>>>(n, mode, nn, nacc, dc);
+          CK(cudaDeviceSynchronize());
+          long long c = 0; CK(cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost));
+          printf("mma rate %-22s N=%3d, %d accumulators: %.1f cycles / MMA\n", nm[mode], nn, nacc, (double)c / n);
+        }
   }
   printf(ok ? "ALL CORRECTNESS TESTS PASSED\n" : "SOME CORRECTNESS TESTS FAILED\n");
   return ok ? 0 : 1;
