@@ -87,11 +87,13 @@ def lib():
         _lib.dq_la_nchunk.argtypes = [ctypes.c_int]
         _lib.dq_gemm_last_error.restype = ctypes.c_int
         _lib.dq_gemm_last_error.argtypes = []
+        _lib.dq_la_tc_last_error.restype = ctypes.c_int
+        _lib.dq_la_tc_last_error.argtypes = [ctypes.POINTER(ctypes.c_uint)]
     return _lib
 
 
 def exported_symbols():
-    return sorted(list(_SIGS) + ["dq_la_nchunk", "dq_gemm_last_error"])
+    return sorted(list(_SIGS) + ["dq_la_nchunk", "dq_gemm_last_error", "dq_la_tc_last_error"])
 
 
 def _ptr(x):
@@ -106,9 +108,15 @@ def _ptr(x):
     return x.data_ptr()
 
 
+_OK_DTYPES = (torch.float32, torch.bfloat16, torch.int32, torch.int64)
+_F64_ARGS = {"dq_sumsq", "dq_clip_coef", "dq_mse"}   # the only entry points with a double* (accumulators)
+
+
 def call(name, *args, allow=()):
-    """Launch `name` on torch's current CUDA stream.  Raises on a non-zero return code (codes listed in `allow`
-    are returned to the caller instead: "shape not covered by this kernel")."""
+    """Launch `name` on the current CUDA stream OF THE DEVICE THE TENSORS LIVE ON.  Raises on a non-zero return code
+    (codes listed in `allow` are returned to the caller instead: "shape not covered by this kernel"), on tensors that
+    are spread over several devices, and on dtypes no kernel of the library takes (fp16, int8, ...; the per-argument
+    element type is the one include/dquartic_b200.h declares - callers pass fp32 unless the header says otherwise)."""
     global launches, calls
     sig, nk = _SIGS[name]
     fn = getattr(lib(), name)
@@ -116,8 +124,17 @@ def call(name, *args, allow=()):
         raise TypeError(f"{name}: expected {len(sig) - 1} arguments, got {len(args)}")
     conv = []
     keep = []
+    dev = None
     for c, a in zip(sig, args):
         if c == "p":
+            if isinstance(a, torch.Tensor):
+                if a.dtype not in _OK_DTYPES and not (a.dtype == torch.float64 and name in _F64_ARGS):
+                    raise NativeError(f"{name}: unsupported tensor dtype {a.dtype}")
+                if a.is_cuda:
+                    if dev is None:
+                        dev = a.device
+                    elif a.device != dev:
+                        raise NativeError(f"{name}: tensors on different devices ({dev} and {a.device})")
             conv.append(_ptr(a))
         elif c == "h":
             arr = (ctypes.c_int * len(a))(*[int(v) for v in a])
@@ -127,8 +144,13 @@ def call(name, *args, allow=()):
             conv.append(float(a))
         else:
             conv.append(int(a))
-    conv.append(torch.cuda.current_stream().cuda_stream)
-    rc = fn(*conv)
+    if dev is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):   # kernels, their static per-device state and the stream all belong to `dev`
+            conv.append(torch.cuda.current_stream(dev).cuda_stream)
+            rc = fn(*conv)
+    else:
+        conv.append(torch.cuda.current_stream().cuda_stream)
+        rc = fn(*conv)
     if rc != 0 and rc in allow:
         return rc
     if rc != 0:
@@ -148,6 +170,16 @@ def _cuda_err(rc):
 
 def la_nchunk(L):
     return int(lib().dq_la_nchunk(int(L)))
+
+
+def la_tc_last_error():
+    """None when the tcgen05 LinearAttention pipelines ran clean since the last call, else the timeout record
+    (wait code, blockIdx.x, blockIdx.y, threadIdx.x, barrier address, parity).  Synchronises with the device."""
+    out = (ctypes.c_uint * 6)()
+    rc = int(lib().dq_la_tc_last_error(out))
+    if rc == 0:
+        return None
+    return (rc,) + tuple(int(v) for v in out)
 
 
 def gemm_last_error():

@@ -104,6 +104,10 @@ def train(config_path, parquet_directory, ms2_data_path, ms1_data_path, batch_si
     if world > 1:  # identical initial weights on every rank
         torch.distributed.broadcast(model.flat_params(), src=0)
         model.mark_params_modified()
+        # ... but DIFFERENT timestep / noise streams: train_step draws t and the noise from torch's default CPU / CUDA
+        # generators, whose seed is the same constant in every fresh process.  (The harness mixes the epoch in on
+        # resume, see ModelInterface._run_epochs.)
+        torch.manual_seed(1234 + rank)
 
     diffusion_model = DDIMDiffusionModel(
         model_class=model, num_timesteps=config["model"]["num_timesteps"],

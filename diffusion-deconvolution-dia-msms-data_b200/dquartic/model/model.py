@@ -124,8 +124,10 @@ class DDIMDiffusionModel(ModelInterface):
     # ------------------------------------------------------------------------------------------ forward process
     def q_sample(self, x_0, t, noise=None):
         """sqrt(ab[t]) * x_0 + sqrt(1 - ab[t]) * noise (model.py:225-242); x_0 is taken as given (already normalised)."""
+        x_0 = x_0.float()   # the kernels compute in fp32 (a float64 tensor must not be reinterpreted)
         if noise is None:
             noise = torch.randn_like(x_0)
+        noise = noise.float()
         b = x_0.shape[0]
         out = torch.empty_like(x_0, memory_format=torch.contiguous_format)
         N.call("dq_qsample", x_0.contiguous(), noise.contiguous(), t.to(torch.long).contiguous(), self.alpha_bars, out,
@@ -157,6 +159,7 @@ class DDIMDiffusionModel(ModelInterface):
             raise ValueError(f"Unknown pred_type: {self.pred_type}")
         batch_size = x_t.size(0)
         t = int(t)
+        x_t = x_t.float()
         t_tensor = torch.full((batch_size,), t, device=x_t.device, dtype=torch.long)
         sa, s1m, sap, s1mp = self._step_coefs(t)
         out = self.model(x_t, t_tensor, init_cond, attn_cond)
@@ -204,7 +207,8 @@ class DDIMDiffusionModel(ModelInterface):
             t = torch.randint(0, self.num_timesteps, (batch_size,), device=dev).long()
         else:
             t = t.to(dev).long()
-        noise = torch.randn_like(x_0) if noise is None else self.normalize(noise)
+        x_0 = x_0.float()
+        noise = torch.randn_like(x_0) if noise is None else self.normalize(noise.float())
         ms2_n = self.normalize(ms2_cond) if ms2_cond is not None else None
         ms1_n = self.normalize(ms1_cond) if ms1_cond is not None else None
         x_t = self._q_sample_fused(x_0.float(), t, noise)

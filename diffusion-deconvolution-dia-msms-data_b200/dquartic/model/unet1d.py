@@ -351,8 +351,42 @@ class UNet1d(nn.Module):
         return self._gflat[self.offsets[name]: self.offsets[name] + n]
 
     # ---------------------------------------------------------------------------------------------- bf16 operands
+    def _bf16_sources(self):
+        """Names of the fp32 parameters that have bf16 GEMM-operand copies."""
+        return [f"{blk}.{bl}.proj.weight" for blk in ("mid_block1", "mid_block2") for bl in ("block1", "block2")] + \
+            ["mid_attn.fn.fn.to_qv.weight", "mid_attn.fn.fn.to_out.weight"]
+
+    def __deepcopy__(self, memo):
+        """copy.deepcopy(net): the copy's Parameters must alias ITS flat buffer (a member-wise deep copy would leave
+        them as independent tensors, and the kernels read the flat buffer)."""
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        skip = {"_flat", "_gflat", "_bf16", "_params", "_modules", "_parameters"}
+        nn.Module.__init__(new)
+        for k, v in self.__dict__.items():
+            if k in skip:
+                continue
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        new._init_device = self._flat.device
+        new._register()
+        with torch.no_grad():
+            new._flat.copy_(self._flat)
+        new._gflat = None
+        new._bf16 = {}
+        new._bf16_version = -1
+        for name, par in self._params.items():
+            new._params[name].requires_grad_(par.requires_grad)
+        new.training = self.training
+        return new
+
     def _refresh_bf16(self):
-        ver = (self._flat._version, self._manual_version, self._flat.data_ptr())
+        # The parameters' OWN version counters are part of the key: after .to(device) / _apply the Parameters are
+        # re-pointed with `par.data = view`, which gives them counters of their own, so an in-place update that does
+        # not go through FusedAdamW / load_state_dict (torch.optim.*, nn.init, EMA copy_, p.mul_) bumps only those.
+        ver = (self._flat._version, self._manual_version, self._flat.data_ptr(),
+               tuple(self._params[k]._version for k in self._bf16_sources()))
         if self._bf16_version == ver:
             return
         Nm = self.mid_channels

@@ -195,6 +195,9 @@ class DeviceBatchLoader:
         N.call("dq_multiplex", ms2, ms1, self.dtype_code, pidx, stats, float(weights[0]), float(weights[1]), x0, other,
                cond, m1, m2, nb, self.rt * self.mz, self.rt)
         if slot is not None:
+            # pidx was allocated on the copy stream: tell the caching allocator the compute stream reads it, or the
+            # block could be handed to the next prefetch() while the multiplex kernel is still queued
+            pidx.record_stream(torch.cuda.current_stream(dev))
             ev2 = torch.cuda.Event()
             ev2.record(torch.cuda.current_stream(dev))
             self._free_ev[slot] = ev2

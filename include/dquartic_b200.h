@@ -100,6 +100,10 @@ int dq_sample_dot(const float* d, const float* c, float* dscale, float* dshift, 
  * sd (R,128), dxnq (R,C,L).  Saved by forward for backward: msm (R,128,2+CP) = [max, sum, Ms], gmat (R,C,128),
  * ypre (R,C,L). */
 int dq_la_nchunk(int L);
+/* Pipeline-timeout record of the tcgen05 LinearAttention kernels (csrc/linattn_tc.cu): returns 0 when clean, 1 when an
+ * mbarrier wait timed out since the last call (out6 = 0x80000000 | wait code, blockIdx.x, blockIdx.y, threadIdx.x,
+ * barrier address, parity); -1 on a CUDA error.  Synchronises with the device; reading clears the record. */
+int dq_la_tc_last_error(unsigned int* out6);
 int dq_linattn_fwd(const float* x, const float* g_pre, const float* wqkv, const float* wout, const float* bout,
                    const float* g_out, float* part, float* msm, float* gmat, float* ypre, float* out, int C, int R,
                    int L, void* stream);
