@@ -9,14 +9,19 @@ q_sample, U-Net forward/backward (gradient accumulation over 4 micro-batches of 
 N > 1 (torchrun): weak scaling, 256 samples per GPU, one bucketed NCCL gradient all-reduce per step.
 
 One JSON line on rank 0:
-  value      train samples/s, inputs resident in HBM (pool in HBM, pair indices pre-uploaded)
+  value      train samples/s, inputs resident in HBM (slice pool of 520 in HBM; pair drawing, multiplexing / normalisation
+             kernel, q_sample, forward / backward, clip + AdamW all inside the timed loop)
   e2e        the same through the public API with HOST buffers: pool in pinned host memory, per-step H2D copy of
              the drawn raw slices, loss read back to the host every step
   roofline   dominant kernel (measured live with CUDA events), see DESIGN.md
-  cpu_baseline  the oracle port (torch fp32 CPU restatement of the reference) on the host cores, bounded sample
-  sampling   DDIM-sampled MS2 maps/s (50 steps), extra to the contract
-`--impl reference` times the reference's CPU implementation of the same step (the oracle port: the reference is
-pure Python and /root/reference does not exist on the GPU box), one sample per step.
+  cpu_baseline        the UNMODIFIED reference (vendored by oracle/make_ref.py into oracle/_ref) on the host cores, bounded
+                      sample; the oracle port if oracle/_ref is absent
+  gpu_eager_baseline  the same reference code on the B200 in eager fp32 ("stock PyTorch on B200"), b = 1 and
+                      the largest batch <= 8 that fits
+  sampling   DDIM-sampled MS2 maps/s (50 steps) through DDIMDiffusionModel.sample_windows, windows sharded over the ranks
+  strong     (N > 1) the same step at a GLOBAL batch of 256 (256 / N per GPU); dp_check: N-rank gradient vs one rank on
+             the union batch
+`--impl reference` times the reference's own `_train_one_batch` (oracle/_ref) on the host cores, one sample per step.
 """
 import argparse
 import json
@@ -96,24 +101,79 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
+def _ref_path():
+    p = os.path.join(ROOT, "oracle", "_ref")
+    return p if os.path.isdir(os.path.join(p, "dquartic", "model")) else None
+
+
+def ref_train_step_rate(torch, device, batch, steps, warmup):
+    """The UNMODIFIED reference (oracle/_ref, vendored by oracle/make_ref.py): DDIMDiffusionModel._train_one_batch =
+    zero_grad, train_step (q_sample, U-Net forward, MSE), backward, clip_grad_norm_(10), AdamW.step, loss.item() on
+    `device`, full-size default model, fp32.  Returns (samples/s, description)."""
+    rp = _ref_path()
+    if rp not in sys.path:
+        sys.path.insert(0, rp)
+    import importlib
+    mods = [m for m in list(sys.modules) if m == "dquartic" or m.startswith("dquartic.")]
+    saved = {m: sys.modules.pop(m) for m in mods}      # our package has the same name: import the reference's, then restore
+    try:
+        unet = importlib.import_module("dquartic.model.unet1d")
+        model = importlib.import_module("dquartic.model.model")
+    finally:
+        for m in list(sys.modules):
+            if m == "dquartic" or m.startswith("dquartic."):
+                sys.modules.pop(m)
+        sys.modules.update(saved)
+        sys.path.remove(rp)
+    torch.manual_seed(0)
+    net = unet.UNet1d(dim=DEFAULT_CFG["dim"], channels=1, dim_mults=tuple(DEFAULT_CFG["dim_mults"]), conditional=True,
+                      init_cond_channels=1, attn_cond_channels=1, tfer_dim_mult=620, downsample_dim=MZ, simple=True).to(device)
+    d = model.DDIMDiffusionModel(net, device=device)
+    d._set_lr(1e-5)
+    g = torch.Generator().manual_seed(0)
+    x0 = (torch.rand(batch, RT, MZ, generator=g) * (torch.rand(batch, RT, MZ, generator=g) < 0.02)).to(device)
+    other = (torch.rand(batch, RT, MZ, generator=g) * (torch.rand(batch, RT, MZ, generator=g) < 0.02)).to(device)
+    cond = 0.5 * x0 + 0.5 * other
+    ms1 = torch.rand(batch, RT, generator=g).to(device)
+    times = []
+    for it in range(warmup + steps):
+        if device != "cpu":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        d._train_one_batch(x0, ms2_cond=cond, ms1_cond=ms1)     # ends in loss.item(): a device sync
+        if device != "cpu":
+            torch.cuda.synchronize()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    del d, net
+    return batch / mean, (f"{len(times)} optimizer step(s) at batch {batch} of the unmodified reference "
+                          f"(_train_one_batch: fwd+bwd+clip+AdamW), full-size model, fp32, {mean:.3f} s/step")
+
+
 def run_reference(args, rank, world):
-    """The reference's CPU implementation of the training step (oracle port), one sample per step."""
+    """The reference's own CPU implementation of the training step, one sample per step, all host threads."""
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
-    import dquartic_oracle as O
 
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    v, sample = cpu_train_step_rate(O, torch, steps=args.steps, warmup=args.warmup)
+    if _ref_path():
+        v, sample = ref_train_step_rate(torch, "cpu", 1, steps=args.steps, warmup=args.warmup)
+        kind = "reference"
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import dquartic_oracle as O
+        v, sample = cpu_train_step_rate(O, torch, steps=args.steps, warmup=args.warmup)
+        kind = "port"
     ms = 1000.0 / v
     line = {
         "impl": "reference", "metric": "train_samples_per_s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(1, 1, per_gpu_batch=1),
-        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -184,10 +244,13 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU per optimizer step")
     ap.add_argument("--micro-batch", type=int, default=64)
-    ap.add_argument("--pool", type=int, default=96, help="synthetic pool size (slices)")
+    ap.add_argument("--pool", type=int, default=520, help="synthetic pool size (slices; 520 = the notebooks' pool, SURVEY.md §8d)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sampling", action="store_true")
-    ap.add_argument("--sample-windows", type=int, default=32)
+    ap.add_argument("--sample-windows", type=int, default=1024, help="DDIM windows per GPU streamed through sample_windows")
+    ap.add_argument("--sample-chunk", type=int, default=32)
+    ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -255,16 +318,13 @@ def main():
     # ---- value: inputs resident in HBM when the timed region starts
     def run_loop(n_warm, n_timed, e2e):
         loader = pin_loader if e2e else hbm_loader
-        batches = None
-        if not e2e:
-            batches = [loader.make_batch(draw(loader), want_cond=True) for _ in range(min(2, n_warm + n_timed))]
         for i in range(n_warm):
             if e2e:
                 x0, m1, other, m2 = loader.make_batch(draw(loader))
                 x0, m1c, cond = ddim._mix_to_device(x0, m1, other, (0.5, 0.5))
                 ddim._train_one_batch(x0, cond, m1c)
             else:
-                x0, m1, other, m2, cond = batches[i % len(batches)]
+                x0, m1, other, m2, cond = loader.make_batch(draw(loader), want_cond=True)
                 ddim._train_one_batch(x0, cond, m1)
         barrier()
         l0 = N.launches
@@ -285,7 +345,9 @@ def main():
                 x0, m1c, cond = ddim._mix_to_device(x0, m1, other, (0.5, 0.5))
                 ddim._train_one_batch(x0, cond, m1c)  # returns loss.item(): device -> host read every step
             else:
-                x0, m1, other, m2, cond = batches[i % len(batches)]
+                # pool resident in HBM: pair drawing (host, python `random` as in the reference), then ONE kernel chain
+                # gathers / normalises / mixes the 256 drawn pairs; all inside the timed region
+                x0, m1, other, m2, cond = loader.make_batch(draw(loader), want_cond=True)
                 ddim._train_one_batch(x0, cond, m1)
         ev1.record()
         barrier()
@@ -311,22 +373,72 @@ def main():
     d2h = 4
 
     extra = {}
+    if world > 1 and not args.no_strong:
+        # strong scaling: the SAME global batch of 256 spread over the ranks (SURVEY.md §8d asks for both)
+        Bw, mbw = B, ddim.micro_batch
+        B = max(1, Bw // world)
+        ddim.micro_batch = min(mbw, B)
+        hbm_loader.batch_size = B
+        ms_s, _ = run_loop(2, args.steps, e2e=False)
+        strong = {"global_batch": B * world, "per_gpu_batch": B, "ms_per_step": ms_s / args.steps,
+                  "value": B * world / (ms_s / args.steps / 1000.0), "unit": "samples/s", "scaling": "strong",
+                  "note": "efficiency = value / (the N = 1 line's value): computed by the reader, not here"}
+        B, ddim.micro_batch = Bw, mbw
+        hbm_loader.batch_size = B
+        dp = dp_check(torch, dist, ddim, net, dev, rank, world)
+        if rank == 0:
+            extra["strong"] = strong
+            extra["dp_check"] = dp
     if rank == 0:
         extra["roofline"] = dominant_kernel_roofline(torch, N, net, dev, min(B, args.micro_batch))
         extra["step_breakdown"] = {"train_gflop_per_sample": 3 * FWD_GFLOP_PER_SAMPLE,
                                    "achieved_tflops_whole_step": 3 * FWD_GFLOP_PER_SAMPLE * B / ms_step,
                                    "frac_of_bf16_sustained_peak": 3 * FWD_GFLOP_PER_SAMPLE * B / ms_step / peaks()["tensor_sustained"]}
     if not args.no_sampling:
-        extra_s = sampling_rate(torch, dist, ddim, hbm_loader, ds, dev, world, args.sample_windows)
+        extra_s = sampling_rate(torch, dist, ddim, hbm_loader, ds, dev, rank, world, args.sample_windows, args.sample_chunk)
         if rank == 0:
             extra["sampling"] = extra_s
+    tc_err = N.la_tc_last_error()
+    if tc_err is not None:
+        raise RuntimeError(f"tcgen05 LinearAttention pipeline timed out during the bench: {tc_err}")
+    if rank == 0 and world == 1 and not args.no_eager_baseline and _ref_path():
+        # "stock PyTorch on B200": the unmodified reference in eager fp32 on the same GPU.  Our model and optimizer
+        # state are released first (the eager reference materialises ~35 GB of activations per sample).
+        hbm_loader.ms2 = pin_loader.ms2 = None
+        del ddim, net
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        eager = []
+        for bb in (1, 2, 4, 8):
+            try:
+                v, sample = ref_train_step_rate(torch, "cuda", bb, steps=2, warmup=1)
+                eager.append({"batch": bb, "value": v, "unit": "samples/s", "sample": sample})
+            except torch.cuda.OutOfMemoryError:
+                eager.append({"batch": bb, "value": None, "note": "out of memory (180 GB) in eager fp32"})
+                break
+            except RuntimeError as e:   # the reference only runs at batch 1 (SURVEY.md finding 1)
+                eager.append({"batch": bb, "value": None, "note": "the reference raises: " + str(e).splitlines()[0][:160]})
+                break
+            finally:
+                gc.collect()
+                torch.cuda.empty_cache()
+        extra["gpu_eager_baseline"] = {"kind": "reference", "dtype": "f32", "device": torch.cuda.get_device_name(dev),
+                                       "runs": eager,
+                                       "note": "the reference only runs at batch 1 (SURVEY.md finding 1: its conditioning "
+                                               "concat breaks for b > 1); the attempt at b = 2 is recorded as it fails"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import dquartic_oracle as O
         cores = os.cpu_count()
         torch.set_num_threads(cores)
-        v, sample = cpu_train_step_rate(O, torch, steps=1, warmup=0)
-        extra["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
+        if _ref_path():
+            v, sample = ref_train_step_rate(torch, "cpu", 1, steps=1, warmup=0)
+            kind = "reference"
+        else:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import dquartic_oracle as O
+            v, sample = cpu_train_step_rate(O, torch, steps=1, warmup=0)
+            kind = "port"
+        extra["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample}
 
     if rank == 0:
         line = {
@@ -454,28 +566,95 @@ def dominant_kernel_roofline(torch, N, net, dev, n_samples=64):
     return main
 
 
-def sampling_rate(torch, dist, ddim, loader, ds, dev, world, windows):
-    """DDIM sampling (50 steps) of `windows` windows per GPU, sharded by window, no collective."""
+def sampling_rate(torch, dist, ddim, loader, ds, dev, rank, world, windows, chunk):
+    """BASELINE configs[3]: DDIM sampling (50 steps) of `windows` DIA windows PER GPU through the product driver
+    `DDIMDiffusionModel.sample_windows`: windows sharded over the ranks in contiguous blocks, x_T from (seed, window id),
+    the 50-step loop of a chunk replayed from one CUDA graph, results copied to pinned host memory, no collective.  The
+    conditioning of window w is the multiplexed pair (w mod 64) of the synthetic pool (the pool is reused cyclically)."""
     ds.reset_epoch()
-    x0, m1, other, m2, cond = loader.make_batch(loader.draw(windows), want_cond=True)
-    xT = torch.randn_like(x0)
-    ddim.model.eval()
-    with torch.no_grad():
-        ddim.sample(xT, cond, m1, num_steps=2)
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        ddim.sample(xT, cond, m1, num_steps=50)
-        ev1.record()
-        torch.cuda.synchronize()
+    x0p, m1p, otherp, m2p, condp = loader.make_batch(loader.draw(64), want_cond=True)
+    del x0p, otherp, m2p
+
+    def cond_fn(ids):
+        idx = torch.tensor([w % 64 for w in ids], device=dev)
+        return condp[idx], m1p[idx]
+
+    total = windows * world
+    ids = list(range(total))
+    ddim.sample_windows(ids[: 2 * chunk * world], cond_fn, seed=1234, num_steps=2, chunk=chunk, rank=rank, world=world)  # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    got, maps = ddim.sample_windows(ids, cond_fn, seed=1234, num_steps=50, chunk=chunk, rank=rank, world=world)
+    ev1.record()
+    torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
     ddim.model.train()
-    return {"metric": "ddim_maps_per_s", "value": windows * world / (ms / 1000.0), "unit": "maps/s", "num_steps": 50,
-            "windows_per_gpu": windows, "ms_total": ms}
+    v = total / (ms / 1000.0)
+    tf = v * 50 * FWD_GFLOP_PER_SAMPLE / 1e3 / world   # TFLOP/s per GPU of reference-algorithmic forward work
+    return {"metric": "ddim_maps_per_s", "value": v, "unit": "maps/s", "num_steps": 50, "windows_per_gpu": windows,
+            "windows_total": total, "chunk": chunk, "ms_total": ms, "d2h_bytes": int(maps.numel() * 4),
+            "forward_tflops_per_gpu": tf, "frac_of_bf16_sustained_peak": tf / peaks()["tensor_sustained"],
+            "note": "forward = 212.87 GFLOP per map and step (SURVEY.md §8d); includes x_T generation, the device -> "
+                    "pinned-host copy of every map and the CUDA-graph capture of the first chunk"}
+
+
+def dp_check(torch, dist, ddim, net, dev, rank, world, per_rank=2):
+    """N-rank data-parallel step vs ONE rank on the union batch (same injected t / noise): cosine of the whole flat
+    gradient (mean over the union batch).  lr = 0, so parameters stay put.  Runs on every rank; rank 0 reports."""
+    import copy
+    g = torch.Generator().manual_seed(4321)
+    n = per_rank * world
+    x0 = (torch.rand(n, RT, MZ, generator=g) * (torch.rand(n, RT, MZ, generator=g) < 0.02)).to(dev)
+    cond = (0.5 * x0 + 0.5 * (torch.rand(n, RT, MZ, generator=g) * (torch.rand(n, RT, MZ, generator=g) < 0.02)).to(dev))
+    m1 = torch.rand(n, RT, generator=g).to(dev)
+    noise = torch.rand(n, RT, MZ, generator=g).to(dev)       # the harness maps injected noise n -> 2 n - 1
+    t = torch.randint(0, 1000, (n,), generator=g).to(dev)
+    lr = ddim.optimizer.param_groups[0]["lr"]
+    ddim.optimizer.param_groups[0]["lr"] = 0.0
+    ddim.optimizer.param_groups[0]["weight_decay"] = 0.0
+    mb = ddim.micro_batch
+    ddim.micro_batch = per_rank
+    sl = slice(rank * per_rank, (rank + 1) * per_rank)
+    ddim._train_one_batch(x0[sl], cond[sl], m1[sl], noise=noise[sl], t=t[sl])
+    gsum = net.flat_grads()[: net.n_trainable_flat].clone()
+    plan = ddim._shard_plan()
+    if plan:                      # sharded exchange: every rank holds the reduced values of its pieces only
+        for (o, cnt) in plan:
+            k = cnt // world
+            dist.all_gather_into_tensor(gsum[o:o + cnt], gsum[o + rank * k:o + (rank + 1) * k].clone())
+    g_dp = gsum / world
+    norm_dp = float(ddim.optimizer.last_grad_norm)
+    # one rank, union batch, no exchange
+    dist_on = ddim._dist_on
+    ddim._dist_on = lambda: False
+    real_allreduce = ddim._allreduce_grads
+    ddim._allreduce_grads = lambda: 1.0
+    real_step = ddim.optimizer.step
+    ddim.optimizer.step = lambda *a, **k: None      # (the sharded optimizer's step is a collective; lr is 0 anyway)
+    res = None
+    if rank == 0:
+        ddim._train_one_batch(x0, cond, m1, noise=noise, t=t)    # micro-batches of per_rank, accumulated
+        g_ref = net.flat_grads()[: net.n_trainable_flat]
+        num = float(torch.dot(g_dp.double(), g_ref.double()))
+        cos = num / float(g_dp.double().norm() * g_ref.double().norm())
+        res = {"ranks": world, "union_batch": n, "flat_gradient_cosine": cos,
+               "max_abs_diff_over_max_abs": float((g_dp - g_ref).abs().max() / g_ref.abs().max()),
+               "sharded_optimizer": bool(plan), "grad_norm_dp": norm_dp}
+    ddim._dist_on = dist_on
+    ddim._allreduce_grads = real_allreduce
+    ddim.optimizer.step = real_step
+    ddim.optimizer.param_groups[0]["lr"] = lr
+    ddim.optimizer.param_groups[0]["weight_decay"] = 0.01
+    ddim.micro_batch = mb
+    dist.barrier()
+    return res
 
 
 if __name__ == "__main__":

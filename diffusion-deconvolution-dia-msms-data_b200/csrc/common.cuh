@@ -34,10 +34,11 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
-// activations: 0 none, 1 SiLU, 2 GELU(erf)
+// activations: 0 none, 1 SiLU, 2 GELU(erf), 3 Softplus (beta 1, threshold 20: torch.nn.Softplus defaults)
 __device__ __forceinline__ float act_fwd(float z, int act) {
   if (act == 1) return z / (1.f + __expf(-z));
   if (act == 2) return 0.5f * z * (1.f + erff(z * 0.70710678118654752440f));
+  if (act == 3) return z > 20.f ? z : log1pf(expf(z));
   return z;
 }
 __device__ __forceinline__ float act_bwd(float z, int act) {  // d act / d z
@@ -50,6 +51,7 @@ __device__ __forceinline__ float act_bwd(float z, int act) {  // d act / d z
     float pdf = 0.39894228040143267794f * __expf(-0.5f * z * z);
     return cdf + z * pdf;
   }
+  if (act == 3) return z > 20.f ? 1.f : 1.f / (1.f + expf(-z));
   return 1.f;
 }
 

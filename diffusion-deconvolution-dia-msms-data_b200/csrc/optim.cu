@@ -31,12 +31,14 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
   }
 }
 
-// norm = sqrt(sumsq); coef = min(1, max_norm / (norm + 1e-6))   (torch.nn.utils.clip_grad_norm_)
-__global__ void clip_coef_kernel(const double* sumsq, float max_norm, float* out /* [0]=norm, [1]=coef */) {
-  float norm = (float)sqrt(*sumsq);
+// norm = gscale sqrt(sumsq); coef = gscale min(1, max_norm / (norm + 1e-6))   (torch.nn.utils.clip_grad_norm_ applied to
+// gscale * g: under data parallelism the buffer holds the SUM over ranks and gscale = 1 / world-size, so the averaging
+// costs no pass over the gradient)
+__global__ void clip_coef_kernel(const double* sumsq, float max_norm, float gscale, float* out /* [0]=norm, [1]=coef */) {
+  float norm = (float)sqrt(*sumsq) * gscale;
   float coef = max_norm / (norm + 1e-6f);
   out[0] = norm;
-  out[1] = coef < 1.f ? coef : 1.f;
+  out[1] = (coef < 1.f ? coef : 1.f) * gscale;
 }
 
 // torch.optim.AdamW single-tensor arithmetic, grads pre-scaled by the clip coefficient read from device memory.
@@ -76,8 +78,8 @@ DQ_API int dq_sumsq(const float* x, long n, double* out, void* stream) {
   DQ_LAUNCH_CHECK();
   return 0;
 }
-DQ_API int dq_clip_coef(const double* sumsq, float max_norm, float* out, void* stream) {
-  clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, max_norm, out);
+DQ_API int dq_clip_coef(const double* sumsq, float max_norm, float gscale, float* out, void* stream) {
+  clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, max_norm, gscale, out);
   DQ_LAUNCH_CHECK();
   return 0;
 }

@@ -81,6 +81,53 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(const float* __restrict_
   }
 }
 
+// DDIM reverse step, pred_type x0 (p_sample 275-289): eps = (x_t - sa*x0) / s1m ; x_prev = last ? x0 : sap*x0 + s1mp*eps
+// (the reference's eager op order, one rounding per op); writes x_prev and eps: 16 B / element
+__global__ void __launch_bounds__(256) ddim_step_x0_kernel(const float* __restrict__ xt, const float* __restrict__ x0p,
+                                                           float* __restrict__ xprev, float* __restrict__ eps_out, float sa,
+                                                           float s1m, float sap, float s1mp, int last, long n) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float x0 = x0p[i];
+    const float e = __fdiv_rn(__fsub_rn(xt[i], __fmul_rn(sa, x0)), s1m);
+    eps_out[i] = e;
+    xprev[i] = last ? x0 : __fadd_rn(__fmul_rn(sap, x0), __fmul_rn(s1mp, e));
+  }
+}
+
+// out = x * s[0], the scale read from device memory (upstream gradient of the MSE node; optimiser-side 1 / world-size)
+__global__ void __launch_bounds__(256) scale_by_kernel(const float* __restrict__ x, const float* __restrict__ s,
+                                                       float* __restrict__ out, long n) {
+  const float k = __ldg(s);
+  const long stride = (long)gridDim.x * blockDim.x;
+  const long n4 = ((n & 3) == 0 && ((((size_t)x) | ((size_t)out)) & 15) == 0) ? n / 4 : 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    v.x *= k; v.y *= k; v.z *= k; v.w *= k;
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+  for (long i = n4 * 4 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = x[i] * k;
+}
+
+// Evaluation metric of the batched predictor: per window, the three sums <a, b>, <a, a>, <b, b> in ONE
+// pass over (prediction, target): 8 B / element; out[s] = {dot, |a|^2, |b|^2} accumulated with atomics (zero it first).
+__global__ void __launch_bounds__(256) cosine_sums_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                          float* __restrict__ out, long n_per_sample) {
+  __shared__ float red[8 * 3];
+  const int s = blockIdx.y;
+  const float* ap = a + (size_t)s * n_per_sample;
+  const float* bp = b + (size_t)s * n_per_sample;
+  float v[3] = {0.f, 0.f, 0.f};
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_sample; i += (long)gridDim.x * blockDim.x) {
+    const float x = ap[i], y = bp[i];
+    v[0] = fmaf(x, y, v[0]);
+    v[1] = fmaf(x, x, v[1]);
+    v[2] = fmaf(y, y, v[2]);
+  }
+  const float tot = block_reduce_vec<3>(v, red);
+  if (threadIdx.x < 3) atomicAdd(out + (size_t)s * 3 + threadIdx.x, tot);
+}
+
 // tail of sample(): x = (x+1)*0.5 ; pred_noise = (cond_n+1)*0.5 - x      (model.py:319-322)
 __global__ void __launch_bounds__(256) sample_finalize_kernel(const float* __restrict__ x, const float* __restrict__ cond_n,
                                                               float* __restrict__ xo, float* __restrict__ pn, long n) {
@@ -156,6 +203,28 @@ DQ_API int dq_ddim_step(const float* xt, const float* eps, float* xprev, float s
                         int last, long n, void* stream) {
   if (n <= 0) return 0;
   ddim_step_kernel<<<grid_for(n, 16), 256, 0, (cudaStream_t)stream>>>(xt, eps, xprev, sa, s1m, sap, s1mp, last, n);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+DQ_API int dq_ddim_step_x0(const float* xt, const float* x0_pred, float* xprev, float* eps_out, float sa, float s1m,
+                           float sap, float s1mp, int last, long n, void* stream) {
+  if (n <= 0) return 0;
+  ddim_step_x0_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(xt, x0_pred, xprev, eps_out, sa, s1m, sap, s1mp, last, n);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+DQ_API int dq_scale_by(const float* x, const float* scale1, float* out, long n, void* stream) {
+  if (n <= 0) return 0;
+  scale_by_kernel<<<grid_for(n, 16), 256, 0, (cudaStream_t)stream>>>(x, scale1, out, n);
+  DQ_LAUNCH_CHECK();
+  return 0;
+}
+DQ_API int dq_cosine_sums(const float* a, const float* b, float* out3, long n_per_sample, int n_samples, void* stream) {
+  if (n_samples <= 0 || n_per_sample <= 0) return 0;
+  int bx = (int)((n_per_sample + 256 * 16 - 1) / (256 * 16));
+  if (bx > 256) bx = 256;
+  dim3 grid((unsigned)bx, (unsigned)n_samples);
+  cosine_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, out3, n_per_sample);
   DQ_LAUNCH_CHECK();
   return 0;
 }

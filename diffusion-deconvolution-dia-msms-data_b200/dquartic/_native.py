@@ -19,6 +19,9 @@ _SIGS = {
     "dq_mix_affine": ("ppffffpls", 1),
     "dq_add_mul": ("pffpls", 1),
     "dq_ddim_step": ("pppffffils", 1),
+    "dq_ddim_step_x0": ("ppppffffils", 1),
+    "dq_scale_by": ("pppls", 1),
+    "dq_cosine_sums": ("ppplis", 1),
     "dq_sample_finalize": ("ppppls", 1),
     "dq_mse": ("ppppfls", 1),
     "dq_add_inplace": ("ppls", 1),
@@ -54,7 +57,7 @@ _SIGS = {
     "dq_attn_core_fwd": ("ppppppiis", 1),
     "dq_attn_core_bwd": ("ppppppppiis", 1),
     "dq_sumsq": ("plps", 1),
-    "dq_clip_coef": ("pfps", 1),
+    "dq_clip_coef": ("pffps", 1),
     "dq_adamw": ("pppplpfffffffs", 1),
     "dq_fill": ("pfls", 1),
     "dq_multiplex": ("ppippffpppppilis", 3),

@@ -62,6 +62,18 @@ def extract(a, t, x_shape):
     return out.reshape(b, *((1,) * (len(x_shape) - 1)))
 
 
+def _sic_loss(x0_like, ms1_n):
+    """MS1 summary-ion-chromatogram loss over the RT profiles (sum / mean / max over mz, each divided by its global
+    maximum, MSE against the normalised MS1 chromatogram): see oracle/dquartic_oracle.py:sic_loss for the definition."""
+    tgt = ms1_n / torch.max(ms1_n)
+    total = None
+    for f in (lambda v: v.sum(-1), lambda v: v.mean(-1), lambda v: v.max(-1).values):
+        sic = f(x0_like)
+        term = torch.mean((sic / torch.max(sic) - tgt) ** 2)
+        total = term if total is None else total + term
+    return total
+
+
 class _MSEFn(torch.autograd.Function):
     """mean((pred - target)^2) with the gradient produced in the same pass (F.mse_loss, model.py:361)."""
 
@@ -79,7 +91,9 @@ class _MSEFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (d,) = ctx.saved_tensors
-        return d * g, None
+        out = torch.empty_like(d)   # d * g in one kernel, the scalar stays on the device (no .item() sync)
+        N.call("dq_scale_by", d, g.reshape(1).float().contiguous(), out, d.numel())
+        return out, None
 
 
 class DDIMDiffusionModel(ModelInterface):
@@ -169,10 +183,12 @@ class DDIMDiffusionModel(ModelInterface):
             N.call("dq_ddim_step", x_t.contiguous(), eps_pred, x_prev, sa, s1m, sap, s1mp, 1 if t == 0 else 0,
                    eps_pred.numel())
             return x_prev, eps_pred
-        # pred_type == "x0": a secondary mode; composed from torch elementwise ops
-        x0_pred = out
-        eps_pred = (x_t - sa * x0_pred) / s1m
-        x_prev = sap * x0_pred + s1mp * eps_pred if t > 0 else x0_pred
+        # pred_type == "x0" (model.py:275-289): one fused kernel, the reference's eager op order
+        x0_pred = out.contiguous()
+        x_prev = torch.empty_like(x0_pred)
+        eps_pred = torch.empty_like(x0_pred)
+        N.call("dq_ddim_step_x0", x_t.contiguous(), x0_pred, x_prev, eps_pred, sa, s1m, sap, s1mp, 1 if t == 0 else 0,
+               x0_pred.numel())
         return x_prev, eps_pred
 
     def sample(self, x_t, ms2_cond=None, ms1_cond=None, num_steps=1000):
@@ -192,13 +208,110 @@ class DDIMDiffusionModel(ModelInterface):
             pred_noise = self.unnormalize(ms2_cond) - x_t
         return x_t, pred_noise
 
+    # ------------------------------------------------------------------------------------------ window-sharded sampling
+    @staticmethod
+    def window_seed(seed, window_id):
+        """Seed of window `window_id`'s Philox stream: x_T depends on (seed, window id) only - not on the number of
+        GPUs, the sharding or the chunking."""
+        return (int(seed) * 0x9E3779B97F4A7C15 + int(window_id) * 0xD1B54A32D192ED03 + 0x2545F4914F6CDD1D) & 0x7FFFFFFFFFFFFFFF
+
+    @staticmethod
+    def shard_windows(n_windows, rank, world):
+        """Contiguous block of window indices [lo, hi) of `rank` (blocks differ by at most one window)."""
+        base, rem = divmod(int(n_windows), int(world))
+        lo = rank * base + min(rank, rem)
+        return lo, lo + base + (1 if rank < rem else 0)
+
+    def sample_windows(self, window_ids, cond_fn, seed=0, num_steps=50, chunk=32, rank=None, world=None, out=None,
+                       return_noise=False, cuda_graph=True):
+        """DDIM-sample the DIA windows `window_ids` (model.py:293-324 per window; model_interface.py:1125-1150 returns
+        item [0] only - here every window is kept).
+
+        Sharding: with `rank` / `world` (default: torch.distributed's, else 0 / 1) this process samples the contiguous
+        block `shard_windows(len(window_ids), rank, world)` of the list; there is NO collective, results stay on the host
+        of each rank.  `cond_fn(ids) -> (ms2_cond (n, rt, mz), ms1_cond (n, rt))` supplies the conditioning of a chunk as
+        tensors on `self.device` (values in [0, 1], as `sample` expects).  x_T of a window is drawn from a generator
+        seeded with `window_seed(seed, id)`.  Windows stream through the sampler `chunk` at a time; the 50-step loop of a
+        full chunk is captured ONCE in a CUDA graph (fixed shapes: the scalar coefficients and timesteps of every step
+        are baked in) and replayed per chunk; results are copied to pinned host memory on a side stream while the next
+        chunk runs.  Returns (ids of this rank, maps (n_local, rt, mz) on the host[, pred_noise])."""
+        dist = torch.distributed
+        if rank is None or world is None:
+            on = dist.is_available() and dist.is_initialized()
+            rank, world = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
+        ids_all = [int(w) for w in window_ids]
+        lo, hi = self.shard_windows(len(ids_all), rank, world)
+        ids = ids_all[lo:hi]
+        dev = torch.device(self.device)
+        self.model.eval()
+        n = len(ids)
+        if n == 0:
+            e = out if out is not None else torch.empty(0)
+            return (ids, e, torch.empty(0)) if return_noise else (ids, e)
+        c2_0, c1_0 = cond_fn(ids[:1])
+        rt, mz = c2_0.shape[1], c2_0.shape[2]
+        if out is None:
+            out = torch.empty((n, rt, mz), dtype=torch.float32).pin_memory()
+        out_noise = torch.empty((n, rt, mz), dtype=torch.float32).pin_memory() if return_noise else None
+        copy_stream = torch.cuda.Stream(device=dev)
+        chunk = max(1, min(int(chunk), n))
+
+        def draw_xT(chunk_ids, buf):
+            for k, w in enumerate(chunk_ids):
+                g = torch.Generator(device=dev)
+                g.manual_seed(self.window_seed(seed, w))
+                buf[k].normal_(generator=g)
+
+        # static buffers of the captured graph
+        xT = torch.empty((chunk, rt, mz), dtype=torch.float32, device=dev)
+        c2 = torch.empty_like(xT)
+        c1 = torch.empty((chunk, rt), dtype=torch.float32, device=dev)
+        graph, res = None, None
+        pending = []
+        with torch.no_grad():
+            for s in range(0, n, chunk):
+                cid = ids[s:s + chunk]
+                nb = len(cid)
+                a, b1 = cond_fn(cid)
+                if nb == chunk:
+                    draw_xT(cid, xT)
+                    c2.copy_(a)
+                    c1.copy_(b1)
+                    if cuda_graph and graph is None and n >= 2 * chunk:
+                        self.sample(xT.clone(), c2, c1, num_steps=min(2, num_steps))   # warm-up outside the capture
+                        torch.cuda.synchronize(dev)
+                        graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph):
+                            res = self.sample(xT, c2, c1, num_steps=num_steps)
+                    if graph is not None:
+                        graph.replay()
+                        x, pn = res
+                    else:
+                        x, pn = self.sample(xT, c2, c1, num_steps=num_steps)
+                else:   # ragged last chunk: eager
+                    xt = torch.empty((nb, rt, mz), dtype=torch.float32, device=dev)
+                    draw_xT(cid, xt)
+                    x, pn = self.sample(xt, a.float().contiguous(), b1.float().contiguous(), num_steps=num_steps)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ev)
+                    out[s:s + nb].copy_(x[:nb], non_blocking=True)
+                    if return_noise:
+                        out_noise[s:s + nb].copy_(pn[:nb], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(copy_stream)
+                if graph is not None:
+                    # the graph's output buffers are overwritten by the next replay: it must wait for this copy
+                    torch.cuda.current_stream(dev).wait_event(done)
+                pending.append(done)
+        for e in pending:
+            e.synchronize()
+        return (ids, out, out_noise) if return_noise else (ids, out)
+
     # ------------------------------------------------------------------------------------------ training step
     def train_step(self, x_0, ms2_cond=None, ms1_cond=None, noise=None, ms1_loss_weight=0.0, t=None):
         """model.py:326-406.  `t` (optional, not in the reference) injects the timesteps for parity tests."""
-        if ms1_loss_weight and ms1_loss_weight > 0.0:
-            raise NotImplementedError(
-                "ms1_loss_weight > 0 raises TypeError in the reference (torch.max(dim=-1) returns a tuple, "
-                "model.py:366-368); the SIC loss is not defined (SURVEY.md §8f-3)")
         if self.pred_type not in ("eps", "x0"):
             raise ValueError(f"Unknown pred_type: {self.pred_type}")
         batch_size = x_0.size(0)
@@ -217,4 +330,11 @@ class DDIMDiffusionModel(ModelInterface):
             primary = _MSEFn.apply(pred, noise)
         else:
             primary = _MSEFn.apply(pred, self.normalize(x_0))
-        return primary * extract(self.loss_weight, t, (batch_size,))
+        loss = primary
+        if ms1_loss_weight and ms1_loss_weight > 0.0:
+            # Secondary mode (default weight 0.0, dquartic_train_config.json:18).  The reference's own code raises
+            # TypeError here (torch.max(dim=-1) returns a tuple, model.py:366-368): the semantics are the ones defined
+            # and documented in oracle/dquartic_oracle.py:sic_loss; small (b, RT) reductions, composed with autograd.
+            x0_like = (x_t - pred) if self.pred_type == "eps" else pred
+            loss = (1 - ms1_loss_weight) * primary + ms1_loss_weight * _sic_loss(x0_like, ms1_n)
+        return loss * extract(self.loss_weight, t, (batch_size,))

@@ -8,8 +8,10 @@ grad-clip 10.0 + AdamW(lr, betas (0.9, 0.999), eps 1e-8, weight_decay 0.01), che
 
 New: the optimizer step is three fused kernels over the flat parameter buffer (`FusedAdamW`); a batch larger than
 `micro_batch` is processed by gradient accumulation; under `torch.distributed` the batch is sharded by sample and
-the flat gradient is all-reduced in buckets (the four 300 M-parameter mid-block buckets are launched as soon as the
-mid-stage backward has produced them, overlapping the long down-path backward); rank 0 writes checkpoints.
+the flat gradient is summed over the ranks in buckets (the four 300 M-parameter mid-block ranges are launched as soon as
+the mid-stage backward has produced them, overlapping the long down-path backward).  Those ranges (99 % of the
+parameters) are REDUCE-SCATTERED: each rank keeps Adam moments for, and updates, 1 / world-size of them and the updated
+pieces are all-gathered in place (ZeRO-1); 1 / world-size is folded into the clip coefficient; rank 0 writes checkpoints.
 Plotting / wandb tables (reference 669-976, 1152-1242) are out of scope.
 """
 import functools
@@ -85,7 +87,13 @@ class CallbackHandler:
 class FusedAdamW(torch.optim.Optimizer):
     """AdamW over the flat parameter buffer of a B200 `UNet1d`: grad-norm, clip coefficient and the update are
     three kernels (dq_sumsq, dq_clip_coef, dq_adamw), no host synchronisation.  `state_dict()` /
-    `load_state_dict()` speak torch.optim.AdamW's per-parameter format so reference checkpoints round-trip."""
+    `load_state_dict()` speak torch.optim.AdamW's per-parameter format so reference checkpoints round-trip.
+
+    Data parallel: the gradient buffer holds the SUM over ranks; `grad_scale = 1 / world-size` is folded into the clip
+    coefficient (no averaging pass).  Sharded mode (`set_sharding`): the ranges listed there were reduce-scattered, this
+    rank owns piece `rank` of each of them and keeps Adam moments for its pieces only (1 / world-size of the state,
+    1 / world-size of the update traffic); the small rest of the buffer is replicated and updated by every rank; the
+    updated pieces are all-gathered in place into the flat parameter buffer."""
 
     def __init__(self, net, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
         self.net = net
@@ -98,12 +106,40 @@ class FusedAdamW(torch.optim.Optimizer):
         self._step = 0
         self._scratch = None
         self.last_grad_norm = None
+        self._shard = None      # (rank, world, [(offset, numel)]) of the reduce-scattered ranges
+        self._segments = None   # [(flat offset, numel, state offset)] this rank updates
+        self._full_state = None
+
+    # ---- layout of the state this rank keeps
+    def set_sharding(self, rank, world, ranges):
+        """Call before the first step.  `ranges`: sorted, disjoint (offset, numel) with numel % world == 0."""
+        if self._m is not None:
+            raise RuntimeError("set_sharding must be called before the optimizer state exists")
+        self._shard = (int(rank), int(world), [(int(o), int(n)) for o, n in sorted(ranges)]) if world > 1 and ranges else None
+
+    def _build_segments(self):
+        n = self.net.n_trainable_flat
+        if self._shard is None:
+            return [(0, n, 0)]
+        rank, world, ranges = self._shard
+        segs, pos, so = [], 0, 0
+        for (o, cnt) in ranges:
+            if o > pos:                       # replicated gap before the sharded range
+                segs.append((pos, o - pos, so)); so += o - pos
+            k = cnt // world
+            segs.append((o + rank * k, k, so)); so += k
+            pos = o + cnt
+        if pos < n:
+            segs.append((pos, n - pos, so)); so += n - pos
+        return segs
 
     def _ensure_state(self):
         flat = self.net.flat_params()
         if self._m is None or self._m.device != flat.device:
-            self._m = torch.zeros_like(flat)
-            self._v = torch.zeros_like(flat)
+            self._segments = self._build_segments()
+            total = sum(c for _, c, _ in self._segments)
+            self._m = torch.zeros(total, dtype=torch.float32, device=flat.device)
+            self._v = torch.zeros(total, dtype=torch.float32, device=flat.device)
             self._sumsq = torch.zeros(1, dtype=torch.float64, device=flat.device)
             self._coef = torch.zeros(2, dtype=torch.float32, device=flat.device)
 
@@ -111,26 +147,74 @@ class FusedAdamW(torch.optim.Optimizer):
         self.net.zero_grad()
 
     @torch.no_grad()
-    def step(self, closure=None, max_grad_norm=None):
+    def step(self, closure=None, max_grad_norm=None, grad_scale=1.0):
         self._ensure_state()
         net = self.net
         g = net.flat_grads()
         p = net.flat_params()
-        n = net.n_trainable_flat
         grp = self.param_groups[0]
         lr, (b1, b2), eps, wd = grp["lr"], grp["betas"], grp["eps"], grp["weight_decay"]
         self._step += 1
         coef = None
-        if max_grad_norm is not None:
+        sharded = self._shard is not None
+        if max_grad_norm is not None or grad_scale != 1.0:
             self._sumsq.zero_()
-            N.call("dq_sumsq", g, n, self._sumsq)
-            N.call("dq_clip_coef", self._sumsq, float(max_grad_norm), self._coef)
+            if sharded:
+                # every element of the buffer counted exactly once over the ranks: own pieces everywhere, the replicated
+                # rest on rank 0 only; then one 8-byte all-reduce
+                rank, world, ranges = self._shard
+                owned = {(o + rank * (cnt // world)) for o, cnt in ranges}
+                for (o, cnt, _) in self._segments:
+                    if o in owned or rank == 0:
+                        N.call("dq_sumsq", g[o:o + cnt], cnt, self._sumsq)
+                torch.distributed.all_reduce(self._sumsq)
+            else:
+                N.call("dq_sumsq", g, net.n_trainable_flat, self._sumsq)
+            big = 3.0e38 if max_grad_norm is None else float(max_grad_norm)
+            N.call("dq_clip_coef", self._sumsq, big, float(grad_scale), self._coef)
             coef = self._coef
             self.last_grad_norm = self._coef[0:1]
         bc1 = 1.0 - b1 ** self._step
         bc2 = 1.0 - b2 ** self._step
-        N.call("dq_adamw", p, g, self._m, self._v, n, coef, lr, b1, b2, eps, wd, lr / bc1, math.sqrt(bc2))
+        for (o, cnt, so) in self._segments:
+            N.call("dq_adamw", p[o:o + cnt], g[o:o + cnt], self._m[so:so + cnt], self._v[so:so + cnt], cnt, coef, lr, b1,
+                   b2, eps, wd, lr / bc1, math.sqrt(bc2))
+        if sharded:
+            rank, world, ranges = self._shard
+            for (o, cnt) in ranges:           # updated pieces -> every rank's flat parameter buffer, in place
+                k = cnt // world
+                torch.distributed.all_gather_into_tensor(p[o:o + cnt], p[o + rank * k:o + (rank + 1) * k])
+        self._full_state = None
         net.mark_params_modified()
+
+    # ---- full-size moments (checkpoints) ----------------------------------------------------------------
+    def _full_moments(self):
+        """(m, v) over the whole flat buffer.  Sharded mode: needs `gather_state()` (a collective) beforehand."""
+        n = self.net.n_trainable_flat
+        if self._shard is None:
+            return self._m, self._v
+        if self._full_state is None:
+            raise RuntimeError("sharded FusedAdamW: call gather_state() on every rank before state_dict()")
+        return self._full_state
+
+    @torch.no_grad()
+    def gather_state(self):
+        """Collective (every rank): assemble the full Adam moments from the shards, for `state_dict()`."""
+        self._ensure_state()
+        if self._shard is None:
+            return
+        rank, world, ranges = self._shard
+        n = self.net.n_trainable_flat
+        full = [torch.zeros(n, dtype=torch.float32, device=self._m.device) for _ in range(2)]
+        owned = {(o + rank * (cnt // world)): (o, cnt) for o, cnt in ranges}
+        for (o, cnt, so) in self._segments:
+            for f, src in zip(full, (self._m, self._v)):
+                f[o:o + cnt].copy_(src[so:so + cnt])
+        for (o, cnt) in ranges:
+            k = cnt // world
+            for f in full:
+                torch.distributed.all_gather_into_tensor(f[o:o + cnt], f[o + rank * k:o + (rank + 1) * k].clone())
+        self._full_state = tuple(full)
 
     # torch.optim.AdamW-compatible (de)serialisation -------------------------------------------------------
     def state_dict(self):
@@ -138,12 +222,14 @@ class FusedAdamW(torch.optim.Optimizer):
         net = self.net
         state = {}
         names = list(net._params.keys())
+        if self._step > 0:
+            m_full, v_full = self._full_moments()
         for idx, name in enumerate(names):
             if not net._params[name].requires_grad or self._step == 0:
                 continue
             state[idx] = {"step": torch.tensor(float(self._step)),
-                          "exp_avg": net._view(self._m, name).clone(),
-                          "exp_avg_sq": net._view(self._v, name).clone()}
+                          "exp_avg": net._view(m_full, name).clone(),
+                          "exp_avg_sq": net._view(v_full, name).clone()}
         groups = [{k: v for k, v in self.param_groups[0].items() if k != "params"}]
         groups[0]["params"] = list(range(len(names)))
         return {"state": state, "param_groups": groups}
@@ -152,15 +238,26 @@ class FusedAdamW(torch.optim.Optimizer):
         self._ensure_state()
         net = self.net
         names = list(net._params.keys())
-        self._m.zero_()
-        self._v.zero_()
+        n = net.n_trainable_flat
+        if self._shard is None:
+            m_full, v_full = self._m, self._v
+            m_full.zero_()
+            v_full.zero_()
+        else:
+            m_full = torch.zeros(net.flat_params().numel(), dtype=torch.float32, device=self._m.device)
+            v_full = torch.zeros_like(m_full)
         step = 0
         for idx, st in sd["state"].items():
             name = names[int(idx)]
-            net._view(self._m, name).copy_(st["exp_avg"])
-            net._view(self._v, name).copy_(st["exp_avg_sq"])
+            net._view(m_full, name).copy_(st["exp_avg"])
+            net._view(v_full, name).copy_(st["exp_avg_sq"])
             step = max(step, int(float(st["step"])))
+        if self._shard is not None:
+            for (o, cnt, so) in self._segments:
+                self._m[so:so + cnt].copy_(m_full[o:o + cnt])
+                self._v[so:so + cnt].copy_(v_full[o:o + cnt])
         self._step = step
+        self._full_state = None
         for k, v in sd["param_groups"][0].items():
             if k != "params":
                 self.param_groups[0][k] = v
@@ -229,6 +326,8 @@ class ModelInterface(object):
             if use_wandb and self._is_rank0():
                 import wandb
                 wandb.log({"epoch": epoch, "train/loss": avg, "learning_rate": lr_now})
+            if isinstance(self.optimizer, FusedAdamW):
+                self.optimizer.gather_state()   # sharded optimizer: collective, every rank (no-op otherwise)
             if self._is_rank0():
                 print(f"[Training] Epoch={epoch+1}, lr={lr_now}, loss={avg}")
                 self.save_checkpoint(lr_scheduler, epoch, avg, self._ckpt_latest(checkpoint_path))
@@ -339,6 +438,9 @@ class ModelInterface(object):
     def _set_optimizer(self, lr):
         if hasattr(self.model, "flat_params"):
             self.optimizer = FusedAdamW(self.model, lr=lr)
+            plan = self._shard_plan()
+            if plan:
+                self.optimizer.set_sharding(torch.distributed.get_rank(), torch.distributed.get_world_size(), plan)
         else:  # an arbitrary user module (not the B200 denoiser): plain torch AdamW as in the reference
             self.optimizer = torch.optim.AdamW(self.model.parameters(), lr=lr)
 
@@ -385,50 +487,81 @@ class ModelInterface(object):
         dist = torch.distributed
         return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
+    def _shard_plan(self):
+        """Flat ranges that are reduce-scattered and updated by one rank each (the four 300 M-parameter mid-block
+        convolutions and the mid attention projections: 99 % of the parameters), or None: plain all-reduce and a
+        replicated optimizer (one GPU, non-NCCL backends, DQ_SHARDED_OPT=0, modules without the flat-buffer API)."""
+        if hasattr(self, "_shard_plan_cache"):
+            return self._shard_plan_cache
+        plan = None
+        dist = torch.distributed
+        if (self._dist_on() and os.environ.get("DQ_SHARDED_OPT", "1") != "0" and hasattr(self.model, "early_grad_ranges")
+                and dist.get_backend() == "nccl"):
+            ws = dist.get_world_size()
+            plan = sorted((int(o), int(n)) for o, n in self.model.early_grad_ranges() if n % ws == 0 and n >= 1024 * ws) or None
+        self._shard_plan_cache = plan
+        return plan
+
+    def _reduce_range(self, g, o, n, works):
+        """Sum the gradient range [o, o + n) over the ranks: reduce-scatter (this rank keeps piece `rank`) if the range is
+        in the shard plan, else an all-reduce in buckets."""
+        dist = torch.distributed
+        plan = self._shard_plan()
+        if plan and (o, n) in plan:
+            ws, rank = dist.get_world_size(), dist.get_rank()
+            k = n // ws
+            works.append(dist.reduce_scatter_tensor(g[o + rank * k:o + (rank + 1) * k], g[o:o + n], op=dist.ReduceOp.SUM,
+                                                    async_op=True))
+            return
+        for s in range(o, o + n, self.grad_bucket_elems):
+            e = min(o + n, s + self.grad_bucket_elems)
+            works.append(dist.all_reduce(g[s:e], op=dist.ReduceOp.SUM, async_op=True))
+
     def _early_allreduce(self, ranges):
         """Called from the denoiser's backward as soon as the mid-stage gradients are final: start their
-        all-reduce (async, NCCL stream) so it overlaps the down-path backward."""
-        dist = torch.distributed
+        reduction (async, NCCL stream) so it overlaps the down-path backward."""
         g = self.model.flat_grads()
         self._early_reduced = list(getattr(self, "_early_reduced", []))
         self._early_works = list(getattr(self, "_early_works", []))
         for (o, n) in ranges:
-            for s in range(o, o + n, self.grad_bucket_elems):
-                e = min(o + n, s + self.grad_bucket_elems)
-                self._early_works.append(dist.all_reduce(g[s:e], op=dist.ReduceOp.SUM, async_op=True))
-            self._early_reduced.append((o, n))
+            self._reduce_range(g, int(o), int(n), self._early_works)
+            self._early_reduced.append((int(o), int(n)))
 
     def _allreduce_grads(self):
-        """Average the flat gradient over ranks in buckets (NCCL over NVLink; gloo in the CPU tests)."""
+        """Sum the flat gradient over the ranks (NCCL over NVLink; gloo in the CPU tests).  Returns the factor that
+        turns the sum into the mean: with the fused optimizer it is folded into the clip coefficient (no pass over the
+        gradient), otherwise the gradient is scaled here and 1.0 is returned."""
         dist = torch.distributed
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return
+            return 1.0
         ws = dist.get_world_size()
         if hasattr(self.model, "flat_grads"):
             g = self.model.flat_grads()[: self.model.n_trainable_flat]
             done = getattr(self, "_early_reduced", [])
             works = []
+            todo = [r for r in (self._shard_plan() or []) if r not in done]   # sharded ranges nobody reduced early
+            covered = sorted(list(done) + todo)
             pos = 0
-            ranges = []
-            for (o, n) in sorted(done):
+            for (o, n) in covered:
                 if o > pos:
-                    ranges.append((pos, o - pos))
+                    self._reduce_range(g, pos, o - pos, works)
                 pos = o + n
             if pos < g.numel():
-                ranges.append((pos, g.numel() - pos))
-            for (o, n) in ranges:
-                for s in range(o, o + n, self.grad_bucket_elems):
-                    e = min(o + n, s + self.grad_bucket_elems)
-                    works.append(dist.all_reduce(g[s:e], op=dist.ReduceOp.SUM, async_op=True))
+                self._reduce_range(g, pos, g.numel() - pos, works)
+            for (o, n) in todo:
+                self._reduce_range(g, o, n, works)
             for w in getattr(self, "_early_works", []) + works:
                 w.wait()
-            g.mul_(1.0 / ws)
             self._early_reduced, self._early_works = [], []
-        else:
-            for p in self.model.parameters():
-                if p.grad is not None:
-                    dist.all_reduce(p.grad)
-                    p.grad.mul_(1.0 / ws)
+            if isinstance(self.optimizer, FusedAdamW):
+                return 1.0 / ws
+            g.mul_(1.0 / ws)
+            return 1.0
+        for p in self.model.parameters():
+            if p.grad is not None:
+                dist.all_reduce(p.grad)
+                p.grad.mul_(1.0 / ws)
+        return 1.0
 
     def _auto_micro_batch(self, x_0):
         """Samples per forward/backward pass when `micro_batch` is not set: the whole batch if its saved activations
@@ -477,9 +610,9 @@ class ModelInterface(object):
             total = lm.detach() if total is None else total + lm.detach()
         if hasattr(self.model, "_wgrad_defer"):
             self.model._wgrad_defer = None
-        self._allreduce_grads()
+        gscale = self._allreduce_grads()
         if isinstance(self.optimizer, FusedAdamW):
-            self.optimizer.step(max_grad_norm=self.max_grad_norm)
+            self.optimizer.step(max_grad_norm=self.max_grad_norm, grad_scale=gscale)
         else:
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.max_grad_norm)
             self.optimizer.step()
@@ -493,8 +626,37 @@ class ModelInterface(object):
                                              num_steps=num_steps)
         return sample[0].cpu().detach().numpy(), pred_noise[0].cpu().detach().numpy()
 
-    def predict_batch(self, x_T, ms2_cond, ms1_cond, num_steps=50):
-        """Batched sampling that keeps every window (the reference drops all but item 0, 1150)."""
+    def predict_batch(self, x_T, ms2_cond, ms1_cond, num_steps=50, target=None):
+        """Batched multi-window prediction that keeps EVERY window (the reference's `_predict_one_batch` returns item
+        [0] only, model_interface.py:1150).  With `target` (the clean maps, values in [0, 1]) it also returns the cheap
+        evaluation metric of SURVEY.md §8f-2: the per-window cosine similarity between prediction and target, from one
+        fused pass (dq_cosine_sums).  Returns (pred, pred_noise) or (pred, pred_noise, cosine (b,))."""
         self.model.eval()
         with torch.no_grad():
-            return self.sample(x_T, ms2_cond=ms2_cond, ms1_cond=ms1_cond, num_steps=num_steps)
+            pred, pred_noise = self.sample(x_T, ms2_cond=ms2_cond, ms1_cond=ms1_cond, num_steps=num_steps)
+            if target is None:
+                return pred, pred_noise
+            return pred, pred_noise, self.cosine_to_target(pred, target)
+
+    @staticmethod
+    def cosine_to_target(pred, target):
+        """Per-window cosine similarity <p, t> / (|p| |t|) of (b, rt, mz) maps, one kernel."""
+        b = pred.shape[0]
+        sums = torch.zeros(b, 3, dtype=torch.float32, device=pred.device)
+        N.call("dq_cosine_sums", pred.float().contiguous(), target.to(pred.device).float().contiguous(), sums,
+               pred.numel() // b, b)
+        return sums[:, 0] / (sums[:, 1].sqrt() * sums[:, 2].sqrt()).clamp_min(1e-30)
+
+    def predict_windows(self, dataloader, mixture_weights=(0.5, 0.5), num_steps=50, seed=0):
+        """`predict` for throughput: every batch item is kept and scored.  Returns a list of dicts
+        {ms2_1, ms1_1, mixture, pred, cosine} per batch (numpy arrays; `cosine` is pred vs ms2_1 per window)."""
+        out = []
+        g = torch.Generator(device=self.device)
+        g.manual_seed(int(seed))
+        for ms2_1, ms1_1, ms2_2, ms1_2 in dataloader:
+            x_0, ms1_cond, ms2_cond = self._mix_to_device(ms2_1, ms1_1, ms2_2, mixture_weights)
+            x_T = torch.empty_like(x_0).normal_(generator=g)
+            pred, _, cos = self.predict_batch(x_T, ms2_cond, ms1_cond, num_steps=num_steps, target=x_0)
+            out.append({"ms2_1": x_0.cpu().numpy(), "ms1_1": ms1_cond.cpu().numpy(), "mixture": ms2_cond.cpu().numpy(),
+                        "pred": pred.cpu().numpy(), "cosine": cos.cpu().numpy()})
+        return out

@@ -26,7 +26,7 @@ from .. import _native as N
 HEADS = 4
 DIM_HEAD = 32
 HD = HEADS * DIM_HEAD
-ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_SOFTPLUS = 0, 1, 2, 3
 
 
 def exists(x):
@@ -153,8 +153,8 @@ class UNet1d(nn.Module):
             raise NotImplementedError("kernels are specialised for 4 heads x 32 (the reference defaults)")
         if channels != 1 or default(init_cond_channels, 0) != 1 or default(attn_cond_channels, 0) != 1:
             raise NotImplementedError("channels / init_cond_channels / attn_cond_channels must be 1 (config schema)")
-        if exists(init_dim) or exists(out_dim) or exists(attn_cond_init_dim) or learned_variance or pos_output_only:
-            raise NotImplementedError("init_dim/out_dim/attn_cond_init_dim/learned_variance/pos_output_only: defaults only")
+        if exists(init_dim) or exists(out_dim) or exists(attn_cond_init_dim) or learned_variance:
+            raise NotImplementedError("init_dim/out_dim/attn_cond_init_dim/learned_variance: defaults only")
         if dropout != 0.0:
             raise NotImplementedError("dropout is 0.0 everywhere in the reference config; the kernels have no RNG")
         if dim % 4 != 0 or dim * max(dim_mults) > 32:
@@ -167,7 +167,9 @@ class UNet1d(nn.Module):
         self.downsample_dim = downsample_dim
         self.downsampled_n = downsample_dim // (2 ** (len(dim_mults) - 1))
         self.out_dim = channels
-        self.final_act = nn.Identity()
+        # reference unet1d.py:1084: Softplus head when pos_output_only (one extra elementwise kernel fwd and bwd)
+        self.pos_output_only = bool(pos_output_only)
+        self.final_act = nn.Softplus() if pos_output_only else nn.Identity()
         self.time_dim = dim * 4
         self.dims = [dim] + [dim * m for m in dim_mults]
         self.in_out = list(zip(self.dims[:-1], self.dims[1:]))
@@ -907,12 +909,18 @@ class UNet1d(nn.Module):
 
         f, sf = self._resnet_fwd("final_res_block", cur, x0, rt, save)
         out, _ = self._conv_fwd(f, None, "final_conv.weight", "final_conv.bias", 1, 1, 0, 1, L, rps=rt)
+        out_pre = None
+        if self.pos_output_only:
+            out_pre = out
+            out = torch.empty_like(out_pre)
+            N.call("dq_act_fwd", out_pre, out, ACT_SOFTPLUS, out.numel())
         out = out.view(b, rt, L)
         if squeeze:
             pass  # the reference also returns (1, rt, mz) for 2-D input ("(b rt) d mz -> b (rt d) mz" with b=1)
         if save:
             T.d = dict(b=b, rt=rt, L=L, tp=tp, SS=self._SS, ic=ic, x=x, x0=x0, ac0=ac0, a1=a1, a1u=a1u, cond_nlc=cond_nlc,
-                       down=saved_down, up=saved_up, sm1=sm1, sma=sma, sm2=sm2, sf=sf, f=f, mid_shape=(d, mzd))
+                       down=saved_down, up=saved_up, sm1=sm1, sma=sma, sm2=sm2, sf=sf, f=f, mid_shape=(d, mzd),
+                       out_pre=out_pre)
         return out, T
 
     # ---------------------------------------------------------------------------------------------- backward
@@ -926,6 +934,10 @@ class UNet1d(nn.Module):
         self._dSS = self._zeros(b, self.ss_total)
         acd = self.dim * 2
         d_out = d_out.contiguous().float().view(R, 1, L)
+        if S.get("out_pre") is not None:   # Softplus head
+            dz = torch.empty_like(d_out)
+            N.call("dq_act_bwd", d_out, S["out_pre"], dz, ACT_SOFTPLUS, dz.numel())
+            d_out = dz
 
         # final conv + final res block
         df, _ = self._conv_bwd(d_out, S["f"], None, "final_conv.weight", "final_conv.bias", 1, 1, 0, 1, rps=rt)
@@ -980,7 +992,7 @@ class UNet1d(nn.Module):
         # one pass over (d, cond, x): dW, db and the per-sample d scale / d shift of the ConditionalScaleShift from raw
         # per-sample correlations (csrc/small.cu); the data gradient of the conditioning channel never exists
         rc = 1
-        if S["ic"].shape[1] == 1 and S["x"].shape[1] == 1:
+        if S["ic"].shape[1] == 1 and S["x"].shape[1] == 1 and not getattr(self, "_force_generic_initconv", False):
             scratch = torch.zeros(b, max(1, self.dim // 4), 88, device=dcur.device, dtype=torch.float32)
             rc = N.call("dq_initconv_bwd", dcur, S["ic"], S["x"], _off_ptr(self._SS[:, ico:]), self.ss_total,
                         self._w("init_conv.weight"), self._gw("init_conv.weight"), self._gw("init_conv.bias"),

@@ -46,16 +46,22 @@ class DIAMSDataset(Dataset):
         import glob
         import pyarrow.parquet as pq
 
-        ms2, ms1 = [], []
+        ms2, ms1, meta = [], [], []
+        cols = ["slice_index", "mz_isolation_target", "ms1_data", "ms2_data", "ms1_shape", "ms2_shape"]
         for f in sorted(glob.glob(os.path.join(parquet_directory, "*.parquet"))):
-            tbl = pq.read_table(f, columns=["ms1_data", "ms2_data", "ms1_shape", "ms2_shape"]).to_pydict()
-            for a1, a2, s1, s2 in zip(tbl["ms1_data"], tbl["ms2_data"], tbl["ms1_shape"], tbl["ms2_shape"]):
+            tbl = pq.read_table(f, columns=cols).to_pydict()
+            for si, mt, a1, a2, s1, s2 in zip(tbl["slice_index"], tbl["mz_isolation_target"], tbl["ms1_data"],
+                                              tbl["ms2_data"], tbl["ms1_shape"], tbl["ms2_shape"]):
                 ms2.append(np.asarray(a2, dtype=np.float32).reshape(tuple(s2)))
                 ms1.append(np.asarray(a1, dtype=np.float32).reshape(tuple(s1)))
+                meta.append((int(si), float(mt)))
         if not ms2:
             raise ValueError(f"no parquet slices found under {parquet_directory}")
         self.ms2_data = np.stack(ms2)
         self.ms1_data = np.stack(ms1)
+        # the reference's parquet pair rule (data_loader.py:141-142): two rows with the same isolation window AND the
+        # same slice index are never paired (the .npy rule is idx_1 != idx_2, which this implies)
+        self.pair_meta = meta
 
     def __len__(self):
         return len(self.ms2_data)
@@ -67,6 +73,9 @@ class DIAMSDataset(Dataset):
             idx_1 = random.randint(0, n - 1)
             idx_2 = random.randint(0, n - 1)
             if idx_1 == idx_2:
+                continue
+            meta = getattr(self, "pair_meta", None)
+            if meta is not None and meta[idx_1] == meta[idx_2]:
                 continue
             pair = tuple(sorted((idx_1, idx_2)))
             if pair in self.used_pairs:

@@ -31,6 +31,13 @@ int dq_add_mul(const float* x, float c, float m, float* y, long n, void* stream)
 /* DDIM reverse step, eta=0, pred_type eps: model.py:273, 283-289. */
 int dq_ddim_step(const float* xt, const float* eps, float* xprev, float sa, float s1m, float sap, float s1mp,
                  int last, long n, void* stream);
+/* pred_type "x0" reverse step (model.py:275-289): eps = (x_t - sa x0)/s1m, x_prev = last ? x0 : sap x0 + s1mp eps. */
+int dq_ddim_step_x0(const float* xt, const float* x0_pred, float* xprev, float* eps_out, float sa, float s1m, float sap,
+                    float s1mp, int last, long n, void* stream);
+/* out[i] = x[i] * scale1[0] (scale read on the device: upstream gradient of the fused MSE node, 1 / world-size). */
+int dq_scale_by(const float* x, const float* scale1, float* out, long n, void* stream);
+/* evaluation metric (model_interface.py:630-667 consumer): out3[s] += {<a_s, b_s>, |a_s|^2, |b_s|^2} per window s. */
+int dq_cosine_sums(const float* a, const float* b, float* out3, long n_per_sample, int n_samples, void* stream);
 /* tail of sample(): model.py:319-322. */
 int dq_sample_finalize(const float* x, const float* cond_n, float* xo, float* pn, long n, void* stream);
 /* sum (eps-noise)^2 into a double accumulator and d_eps = gscale*(eps-noise): F.mse_loss model.py:361. */
@@ -144,7 +151,7 @@ int dq_attn_core_bwd(const float* qv, const float* k, const float* freqs, const 
 
 /* ---- optimizer (model/model_interface.py:1011, 1121-1122) --------------------------------------------- */
 int dq_sumsq(const float* x, long n, double* out, void* stream);
-int dq_clip_coef(const double* sumsq, float max_norm, float* out_norm_coef, void* stream);
+int dq_clip_coef(const double* sumsq, float max_norm, float gscale, float* out_norm_coef, void* stream);
 int dq_adamw(float* p, const float* g, float* m, float* v, long n, const float* coef_ptr, float lr, float b1, float b2,
              float eps, float wd, float step_size, float bc2_sqrt, void* stream);
 int dq_fill(float* p, float v, long n, void* stream);

@@ -406,6 +406,58 @@ def lr_lambda(epoch, warmup, total):
     return max(1e-10, 0.5 * (1.0 + math.cos(math.pi * 0.5 * 2.0 * prog)))
 
 
+# ----------------------------------------------------------------------------- secondary modes
+def sic_loss(x0_like, ms1_cond_n):
+    """MS1 summary-ion-chromatogram loss, model/model.py:364-371 / 379-386 — DEFINED HERE, not restated: the reference
+    loops `func in (torch.sum, torch.mean, torch.max)` with `dim=-1`; `torch.max(x, dim=-1)` returns a (values, indices)
+    tuple, so the reference raises TypeError whenever ms1_loss_weight > 0, and its `func(ms1_cond, dim=-1)` would
+    reduce the (b, RT) chromatogram to (b,).  The evident intent — compare the RT profile of the predicted map with
+    the MS1 chromatogram — is what is implemented: for each reduction f in (sum, mean, max-values) over the mz axis,
+    sic_f = f(x0_like) of shape (b, RT); both profiles are divided by their global maximum (as the reference does)
+    and compared with an MSE over all (b, RT) entries; the three terms add up."""
+    total = x0_like.new_zeros(())
+    tgt = ms1_cond_n / torch.max(ms1_cond_n)
+    for f in (lambda v: v.sum(-1), lambda v: v.mean(-1), lambda v: v.max(-1).values):
+        sic = f(x0_like)
+        total = total + F.mse_loss(sic / torch.max(sic), tgt)
+    return total
+
+
+def train_loss_modes(P, cfg, alpha_bars, x0, ms2_cond, ms1_cond, t, noise, pred_type="eps", ms1_loss_weight=0.0,
+                     pos_output_only=False):
+    """model/model.py:343-404 for every (pred_type, ms1_loss_weight, pos_output_only) combination; returns the (b,)
+    loss vector of the batched semantics (batch-mean primary loss times loss_weight[t_i]) and the network output."""
+    x0n = normalize(x0)
+    c2 = normalize(ms2_cond)
+    c1 = normalize(ms1_cond)
+    x_t = q_sample(alpha_bars, x0n, t, noise)
+    out = unet_forward(P, cfg, x_t, t, c2, c1)
+    if pos_output_only:
+        out = F.softplus(out)                      # model/unet1d.py:1084, 1166
+    if pred_type == "eps":
+        primary = F.mse_loss(out, noise)
+        x0_like = x_t - out                        # model/model.py:367 (the reference's choice, not (x_t - s eps)/a)
+    elif pred_type == "x0":
+        primary = F.mse_loss(out, x0n)
+        x0_like = out
+    else:
+        raise ValueError(f"Unknown pred_type: {pred_type}")
+    loss = primary
+    if ms1_loss_weight > 0.0:
+        loss = (1 - ms1_loss_weight) * primary + ms1_loss_weight * sic_loss(x0_like, c1)
+    return loss * loss_weight_table(alpha_bars, pred_type)[t], out
+
+
+def ddim_update_x0(alpha_bars, x_t, x0_pred, t):
+    """model/model.py:275-289, pred_type == 'x0'."""
+    ab = alpha_bars[t]
+    eps = (x_t - torch.sqrt(ab) * x0_pred) / torch.sqrt(1.0 - ab)
+    if t > 0:
+        abp = alpha_bars[t - 1]
+        return torch.sqrt(abp) * x0_pred + torch.sqrt(1.0 - abp) * eps, eps
+    return x0_pred, eps
+
+
 # ----------------------------------------------------------------------------- sampling (a5)
 def ddim_sample(P, cfg, alpha_bars, x_T, ms2_cond, ms1_cond, num_steps):
     """model/model.py:293-324."""
