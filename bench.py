@@ -151,7 +151,7 @@ def ref_train_step_rate(torch, device, batch, steps, warmup):
                           f"(_train_one_batch: fwd+bwd+clip+AdamW), full-size model, fp32, {mean:.3f} s/step")
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """The reference's own CPU implementation of the training step, one sample per step, all host threads."""
     if rank != 0:
         return
@@ -177,7 +177,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_train_step_rate(O, torch, steps, warmup):
@@ -256,8 +256,18 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the ONE JSON line only: libraries that write to file descriptor 1 (NCCL prints its version there,
+    # the dataset prints an "Info: Loaded .." line as the reference does) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
-        return run_reference(args, rank, world)
+        return run_reference(args, rank, world, emit)
 
     import numpy as np
     import torch
@@ -451,7 +461,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
         }
         line.update(extra)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

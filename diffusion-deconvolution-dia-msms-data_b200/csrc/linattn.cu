@@ -1200,6 +1200,11 @@ static int la_bwd(const LAArgs& a, cudaStream_t st) {
     la_bwd_combine_kernel<C><<<(unsigned)((a.R + kRows - 1) / kRows), 128, smem, st>>>(a, kRows);
     DQ_LAUNCH_CHECK();
   }
+  // DQ_LA_KV_TC=1 selects the hybrid tcgen05-scores + mma.sync-f16 k / v kernel (linattn_tc.cu).  Measured slower than
+  // the mma.sync kernel below (level 0, 8 samples: 0.93 vs 0.81 ms, profiles/r2_la_bwd_kv_tc_*), so it stays opt-in.
+  static int kv_tc = -1;
+  if (kv_tc < 0) { const char* e = getenv("DQ_LA_KV_TC"); kv_tc = (e && e[0] == '1') ? 1 : 0; }
+  if (la_tc_enabled() && kv_tc && (C == 4 || C == 8)) return la_bwd_kv_tc(a, C, st);   // hybrid tcgen05 + mma.sync f16 kernel
   {
     size_t smem = sizeof(float) * (TA<C>::SIZE + C * XT + 4 * SP * T::YS + 4 * 16 * RS + SP + C + (C == 4 ? 4 * C * SP : 0));
     cudaFuncSetAttribute(la_bwd_kv_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
