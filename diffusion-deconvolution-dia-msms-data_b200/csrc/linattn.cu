@@ -1181,7 +1181,10 @@ static int la_bwd(const LAArgs& a, cudaStream_t st) {
   using T = TC<C>;
   dim3 grid((unsigned)a.nchunk, (unsigned)a.R);
   bool q_done = false;
-  if (la_tc_enabled() && C <= 16) {   // tcgen05 / TMEM kernel (linattn_tc.cu)
+  // tcgen05 / TMEM kernel (linattn_tc.cu) where it wins: per launch of a 64-sample micro-batch 9.43 -> 5.89 ms (C = 4),
+  // 3.95 -> 3.24 (C = 8), 1.82 -> 1.18 (C = 12); at C = 16 (L <= 1250: 5-10 tiles per CTA, fixed cost dominates, spills) it
+  // measured 1.21 vs 0.71 ms, so the mma.sync kernel keeps that level (profiles/r2_launches_summary.csv vs r1d)
+  if (la_tc_enabled() && C <= 12) {
     const int rc = la_bwd_q_tc(a, C, st);
     if (rc != 0) return rc;
     q_done = true;
