@@ -147,7 +147,9 @@ class FusedAdamW(torch.optim.Optimizer):
         self.net.zero_grad()
 
     @torch.no_grad()
-    def step(self, closure=None, max_grad_norm=None, grad_scale=1.0):
+    def step(self, closure=None, max_grad_norm=None, grad_scale=1.0, defer_gather=False):
+        """`defer_gather` (sharded mode): leave the parameter all-gathers in flight on the NCCL stream; the network waits
+        for them right before its mid stage (`UNet1d.sync_params`), so they overlap the next step's down path."""
         self._ensure_state()
         net = self.net
         g = net.flat_grads()
@@ -181,9 +183,16 @@ class FusedAdamW(torch.optim.Optimizer):
                    b2, eps, wd, lr / bc1, math.sqrt(bc2))
         if sharded:
             rank, world, ranges = self._shard
+            works = []
             for (o, cnt) in ranges:           # updated pieces -> every rank's flat parameter buffer, in place
                 k = cnt // world
-                torch.distributed.all_gather_into_tensor(p[o:o + cnt], p[o + rank * k:o + (rank + 1) * k])
+                works.append(torch.distributed.all_gather_into_tensor(p[o:o + cnt], p[o + rank * k:o + (rank + 1) * k],
+                                                                      async_op=True))
+            if defer_gather and hasattr(net, "sync_params"):
+                net.__dict__.setdefault("_pending_param_works", []).extend(works)
+            else:
+                for w in works:
+                    w.wait()
         self._full_state = None
         net.mark_params_modified()
 
@@ -612,7 +621,7 @@ class ModelInterface(object):
             self.model._wgrad_defer = None
         gscale = self._allreduce_grads()
         if isinstance(self.optimizer, FusedAdamW):
-            self.optimizer.step(max_grad_norm=self.max_grad_norm, grad_scale=gscale)
+            self.optimizer.step(max_grad_norm=self.max_grad_norm, grad_scale=gscale, defer_gather=True)
         else:
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm=self.max_grad_norm)
             self.optimizer.step()

@@ -300,7 +300,12 @@ class UNet1d(nn.Module):
     def _load_from_state_dict(self, *a, **k):  # pragma: no cover - containers handle their own params
         super()._load_from_state_dict(*a, **k)
 
+    def state_dict(self, *args, **kwargs):
+        self.sync_params()
+        return super().state_dict(*args, **kwargs)
+
     def load_state_dict(self, state_dict, strict=True, assign=False):
+        self.sync_params()
         out = super().load_state_dict(state_dict, strict=strict, assign=False)
         self._manual_version += 1
         return out
@@ -311,7 +316,18 @@ class UNet1d(nn.Module):
 
     # ---------------------------------------------------------------------------------------------- flat accessors
     def flat_params(self):
+        self.sync_params()
         return self._flat
+
+    def sync_params(self):
+        """Make the current stream wait for parameter all-gathers the sharded optimizer left in flight
+        (`FusedAdamW.step(defer_gather=True)`): they overlap the next step's down path, whose parameters are replicated;
+        only the mid-stage weights arrive through them.  Called before anything reads those weights."""
+        works = self.__dict__.get("_pending_param_works")
+        if works:
+            for w in works:
+                w.wait()
+            works.clear()
 
     def flat_grads(self):
         self._ensure_grads()
@@ -362,6 +378,7 @@ class UNet1d(nn.Module):
         """copy.deepcopy(net): the copy's Parameters must alias ITS flat buffer (a member-wise deep copy would leave
         them as independent tensors, and the kernels read the flat buffer)."""
         import copy
+        self.sync_params()
         cls = self.__class__
         new = cls.__new__(cls)
         memo[id(self)] = new
@@ -387,6 +404,7 @@ class UNet1d(nn.Module):
         # The parameters' OWN version counters are part of the key: after .to(device) / _apply the Parameters are
         # re-pointed with `par.data = view`, which gives them counters of their own, so an in-place update that does
         # not go through FusedAdamW / load_state_dict (torch.optim.*, nn.init, EMA copy_, p.mul_) bumps only those.
+        self.sync_params()
         ver = (self._flat._version, self._manual_version, self._flat.data_ptr(),
                tuple(self._params[k]._version for k in self._bf16_sources()))
         if self._bf16_version == ver:
@@ -848,7 +866,6 @@ class UNet1d(nn.Module):
                 raise NotImplementedError("attn_cond must be the (b, rt) MS1 chromatogram")
             ac0 = attn_cond.contiguous().float().view(b, 1, rt)
         time = time.to(torch.long).contiguous().view(b)
-        self._refresh_bf16()
         T = _Tape() if save else None
         tp = self._time_path_fwd(time, b, save)
 
@@ -886,6 +903,7 @@ class UNet1d(nn.Module):
         if d * mzd != self.mid_channels:
             raise ValueError("input length is inconsistent with downsample_dim")
         Xm = cur.view(R, d * mzd)  # [(b rt)][(d mz)]: the reference's rearrange is a view here
+        self._refresh_bf16()       # here, not at entry: a deferred parameter all-gather overlaps the down path above
         m1, sm1 = self._mid_block_fwd("mid_block1", Xm, b, rt, save)
         m2, sma = self._mid_attn_fwd(m1, cond_nlc.view(R, acd), b, rt, save)
         m3, sm2 = self._mid_block_fwd("mid_block2", m2, b, rt, save)

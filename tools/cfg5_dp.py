@@ -3,7 +3,10 @@
 reduce-scatter / all-gather of the mid ranges).  A few optimizer steps on fixed per-rank batches: the loss must fall, the
 ranks must hold identical parameters afterwards, memory and throughput are reported by rank 0.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/cfg5_dp.py [per_gpu_batch] [steps]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/cfg5_dp.py [per_gpu_batch] [steps] [small] [lr]
+
+`small` = the default network (dim 4, RT 34) instead: run it once as is and once with DQ_SHARDED_OPT=0 and compare the printed
+losses digit by digit (the sharded optimizer with its deferred, overlapped parameter all-gather against the replicated one).
 """
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -19,20 +22,24 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-rt, mz = 136, 40000
+small = len(sys.argv) > 3 and sys.argv[3] == "small"
+lr = float(sys.argv[4]) if len(sys.argv) > 4 else 1e-5
+rt, mz = (34, 40000) if small else (136, 40000)
 torch.manual_seed(0)
 t0 = time.time()
-net = UNet1d(dim=8, channels=1, dim_mults=(1, 2, 2, 3, 3, 4, 4), conditional=True, init_cond_channels=1,
+net = UNet1d(dim=4 if small else 8, channels=1, dim_mults=(1, 2, 2, 3, 3, 4, 4), conditional=True, init_cond_channels=1,
              attn_cond_channels=1, downsample_dim=mz, device=dev)
 dist.broadcast(net.flat_params(), src=0)
 net.mark_params_modified()
 d = DDIMDiffusionModel(net, device=dev)
 d.micro_batch = min(b, 4)
-d._prepare_training(1e-5)
+d._prepare_training(lr)
 torch.cuda.synchronize()
 if rank == 0:
-    print(f"init {time.time() - t0:.1f} s, params {net.n_flat:,}, sharded ranges {d._shard_plan()}, "
-          f"moments per rank {d.optimizer._build_segments()[-1][2] + d.optimizer._build_segments()[-1][1]:,} floats, "
+    plan = d._shard_plan()
+    seg = d.optimizer._build_segments()[-1] if plan else None
+    print(f"init {time.time() - t0:.1f} s, params {net.n_flat:,}, sharded ranges {plan}, "
+          f"moments per rank {(seg[2] + seg[1]) if seg else net.n_flat:,} floats, "
           f"mem {torch.cuda.memory_allocated() / 1e9:.1f} GB", flush=True)
 g = torch.Generator(device=dev).manual_seed(3 + rank)
 x0 = torch.rand(b, rt, mz, device=dev, generator=g) * (torch.rand(b, rt, mz, device=dev, generator=g) < 0.02)
@@ -47,7 +54,7 @@ for i in range(steps):
     torch.cuda.synchronize(); dist.barrier(); dt = time.time() - t1
     lt = torch.tensor([loss], device=dev); dist.all_reduce(lt); losses.append(float(lt) / world)
     if rank == 0:
-        print(f"step {i}: mean loss {losses[-1]:.6f} grad-norm {float(d.optimizer.last_grad_norm):.4f} {dt * 1e3:.0f} ms "
+        print(f"step {i}: mean loss {losses[-1]:.9f} grad-norm {float(d.optimizer.last_grad_norm):.4f} {dt * 1e3:.0f} ms "
               f"({b * world / dt:.2f} samples/s on {world} GPUs) max mem {torch.cuda.max_memory_allocated() / 1e9:.1f} GB", flush=True)
 assert all(l == l for l in losses) and losses[-1] < losses[0], losses
 # every rank must hold the same parameters after the sharded update + in-place all-gather
