@@ -443,10 +443,20 @@ __device__ __forceinline__ float cf_dsilu(float z) {
 // Used for COUT >= 8, where the FFMA form of the two contractions (2 * 3 * COUT * cin FMAs per position) is what bounds
 // the kernel.  Fragment k-slots are permuted (slot t <-> channel 2t, slot t+4 <-> channel 2t+1) so that with the row
 // stride TS = 4 (mod 32) every fragment load covers the 32 banks once.
-template <int COUT, int K, int P, int NT, bool EPI, bool BULK, bool RES = false, int NCI = 0>
+// UP2: the forward input was the nearest-x2 upsampling of HALF-rate rows (Upsample = nearest x2 + Conv1d k3,
+// unet1d.py:93-96): x1 / dx1 are (R, c1, L / 2); the half-rate rows are staged (x_up[q] = x[q >> 1] is resolved when the
+// wgrad taps are read) and d x_up is folded pairwise before it is stored - the upsampled tensor and its gradient never
+// exist (they were two extra passes, dq_upsample2x / dq_fold2x, and doubled the x / dx bytes of this kernel).
+// DOWN2: backward of Downsample = Conv1d(k4, stride 2, pad 1) (unet1d.py:110): dy is (R, COUT, L / 2) and its HALF-rate rows
+// are staged; d x[2j] = W1 dy[j] + W3 dy[j-1], d x[2j+1] = W0 dy[j+1] + W2 dy[j]; dW_k = sum_m dy[m] x[2m + k - 1] - no
+// space-to-depth copy of x, no depth-to-space pass over dx, no weight re-packing (dq_s2d / dq_d2s / dq_down_w).
+template <int COUT, int K, int P, int NT, bool EPI, bool BULK, bool RES = false, int NCI = 0, bool UP2 = false,
+          bool DOWN2 = false>
 __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs a) {
   constexpr bool MMA = NCI > 0;
   static_assert(!MMA || (EPI && K == 3), "MMA variant: conv3 with epilogue");
+  static_assert(!UP2 || (!EPI && !RES && !MMA && K == 3 && P >= 2), "UP2: plain conv3, FFMA contractions, pairs per thread");
+  static_assert(!DOWN2 || (!EPI && !RES && !MMA && !UP2 && K == 4 && P >= 2), "DOWN2: plain conv k4 s2, FFMA contractions");
   constexpr int KCO = (COUT + 7) / 8;                    // k8 / n8 tiles over the output channels (rows >= COUT: zero weights)
   constexpr int MCI = (NCI + 1) / 2 > 0 ? (NCI + 1) / 2 : 1;   // m16 tiles over the input channels (phase 3)
   constexpr int TL = NT * P;
@@ -500,6 +510,20 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
       float* st = stage0 + s * stage_floats;
       const bool even = ((a.L | w | l_lo) & 1) == 0 && a.al8;
       for (int row = tid >> 5; row < rows; row += NW) {
+        if ((UP2 && row >= DYR) || (DOWN2 && row < DYR)) {   // half-rate source rows: window [tl0 / 2 - 4, tl0 / 2 + TL / 2 + 4)
+          const int Lh = a.L >> 1, h0 = (tl0 >> 1) - 4;
+          const int h_lo = max(0, h0), h_hi = min(Lh, h0 + TL / 2 + 8), wh = h_hi - h_lo;
+          const float* srch = (DOWN2 ? a.dy + ((size_t)r * COUT + row) * Lh : a.x1 + ((size_t)r * a.c1 + (row - DYR)) * Lh) + h_lo;
+          const uint32_t dsth = cf_smem_u32(st + row * TS + (h_lo - h0));
+          if (((Lh | wh | h_lo) & 1) == 0 && a.al8) {
+            for (int e = (tid & 31) * 2; e < wh; e += 64)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dsth + 4u * (uint32_t)e), "l"(srch + e) : "memory");
+          } else {
+            for (int e = tid & 31; e < wh; e += 32)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dsth + 4u * (uint32_t)e), "l"(srch + e) : "memory");
+          }
+          continue;
+        }
         const float* src;
         if (row < COUT) src = a.dy + ((size_t)r * COUT + row) * a.L;
         else if (row < DYR) src = a.u + ((size_t)r * COUT + (row - COUT)) * a.L;
@@ -532,8 +556,17 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
       const uint32_t bar = s ? bar1 : bar0;
       const int row = (tid >> 5) + NW * (tid & 31);
       if (tid == 0 || row < rows) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (tid == 0) cf_mbar_expect_tx(bar, bytes * (uint32_t)rows);
+      const int Lh = a.L >> 1, h0 = (tl0 >> 1) - 4;
+      const int h_lo = max(0, h0), h_hi = min(Lh, h0 + TL / 2 + 8);
+      const uint32_t bytes_h = (uint32_t)(h_hi - h_lo) * 4u;
+      const uint32_t bytes_x = UP2 ? bytes_h : bytes, bytes_d = DOWN2 ? bytes_h : bytes;
+      if (tid == 0) cf_mbar_expect_tx(bar, bytes_d * (uint32_t)(rows - cin) + bytes_x * (uint32_t)cin);
       float* st = stage0 + s * stage_floats;
+      if (UP2 && row >= DYR && row < rows) {
+        cf_bulk_g2s(cf_smem_u32(st + row * TS + (h_lo - h0)), a.x1 + ((size_t)r * a.c1 + (row - DYR)) * Lh + h_lo, bytes_x, bar);
+      } else if (DOWN2 && row < DYR) {
+        cf_bulk_g2s(cf_smem_u32(st + row * TS + (h_lo - h0)), a.dy + ((size_t)r * COUT + row) * Lh + h_lo, bytes_d, bar);
+      } else
       if (row < rows) {
         const float* src;
         if (row < COUT) src = a.dy + ((size_t)r * COUT + row) * a.L;
@@ -757,8 +790,11 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
       }
     } else {
       // plain conv: du = dy already sits in the stage; zero the non-existent positions and accumulate the bias gradient
+      // (DOWN2: the dy tile has TL / 2 half-rate positions, handled by the first half of the threads)
       const int idx = 4 + P * tid;
-      const int nvalid = a.L - (tl0 + P * tid);
+      const int nvalid = DOWN2 ? (a.L >> 1) - ((tl0 >> 1) + P * tid) : a.L - (tl0 + P * tid);
+      if (DOWN2 && P * tid >= TL / 2) {
+      } else
       if (nvalid >= P) {
 #pragma unroll
         for (int c = 0; c < COUT; ++c) {
@@ -778,7 +814,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
       }
       if (H > 0 && tid < COUT) {
         if (tl0 == 0) du_s[tid * TS + 3] = 0.f;
-        if (a.L <= tl0 + TL) du_s[tid * TS + (a.L - tl0 + 4)] = 0.f;
+        if (a.L <= tl0 + TL) du_s[tid * TS + (DOWN2 ? ((a.L - tl0) >> 1) : (a.L - tl0)) + 4] = 0.f;
       }
     }
     if constexpr (RES) {   // bias gradient of the 1x1 conv; non-existent positions are zeroed for phase 3
@@ -805,7 +841,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
     // x rows: exact zeros at the two out-of-range neighbours a valid du can touch (row start / row end)
     if (H > 0 && tid < cin) {
       if (tl0 == 0) x_t[tid * TS + 3] = 0.f;
-      if (a.L <= tl0 + TL) x_t[tid * TS + (a.L - tl0 + 4)] = 0.f;
+      if (a.L <= tl0 + TL) x_t[tid * TS + (UP2 ? ((a.L - tl0) >> 1) : (a.L - tl0)) + 4] = 0.f;
     }
     __syncthreads();
 
@@ -892,7 +928,10 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
         float* dst;
         const float* add = nullptr;
         int accf;
-        if (cb < a.c1) {
+        if (UP2) {
+          dst = a.dx1 ? a.dx1 + ((size_t)r * a.c1 + cb) * (a.L >> 1) + (l >> 1) : nullptr;
+          accf = a.acc1;
+        } else if (cb < a.c1) {
           dst = a.dx1 ? a.dx1 + ((size_t)r * a.c1 + cb) * a.L + l : nullptr;
           accf = a.acc1;
           if (a.dadd) add = a.dadd + ((size_t)r * a.c1 + cb) * a.L + l;
@@ -907,7 +946,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
         for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int i = 0; i < P; ++i) acc[j][i] = 0.f;
-        if (ok && (add || accf)) {
+        if (!UP2 && ok && (add || accf)) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float* d = dst + (size_t)j * a.L;
@@ -928,6 +967,24 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
             }
           }
         }
+        if constexpr (DOWN2) {
+#pragma unroll 4
+          for (int co = 0; co < COUT; ++co) {
+            float dh[P / 2 + 2];   // dy[co][j0 - 1 .. j0 + P / 2], j0 = (this thread's first position) / 2
+            const float* hb = du_s + co * TS + 4 + ((P * tid) >> 1);
+#pragma unroll
+            for (int e = 0; e < P / 2 + 2; ++e) dh[e] = hb[e - 1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 w4 = *reinterpret_cast<const float4*>(w_s + (co * cin + cb + j) * 4);
+#pragma unroll
+              for (int pp = 0; pp < P / 2; ++pp) {
+                acc[j][2 * pp] = fmaf(dh[pp + 1], w4.y, fmaf(dh[pp], w4.w, acc[j][2 * pp]));
+                acc[j][2 * pp + 1] = fmaf(dh[pp + 2], w4.x, fmaf(dh[pp + 1], w4.z, acc[j][2 * pp + 1]));
+              }
+            }
+          }
+        } else
 #pragma unroll 4
         for (int co = 0; co < COUT; ++co) {
           float dwin[P + 2];   // du[co][pos - 1 .. pos + P]
@@ -962,6 +1019,25 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
               for (int i = 0; i < P; ++i) acc[j][i] = fmaf(yo[i], wj[j], acc[j][i]);
           }
         }
+        if constexpr (UP2) {   // d x[m] = d x_up[2m] + d x_up[2m + 1]: both halves of a pair live in this thread
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float* d = dst + (size_t)j * (a.L >> 1);
+              float f[P / 2];
+#pragma unroll
+              for (int m = 0; m < P / 2; ++m) f[m] = acc[j][2 * m] + acc[j][2 * m + 1];
+              if constexpr (BULK && P == 4) {
+                if (accf) { const float2 v = *reinterpret_cast<const float2*>(d); f[0] += v.x; f[P / 2 - 1] += v.y; }
+                *reinterpret_cast<float2*>(d) = make_float2(f[0], f[P / 2 - 1]);
+              } else {
+#pragma unroll
+                for (int m = 0; m < P / 2; ++m)
+                  if (l + 2 * m < a.L) d[m] = accf ? d[m] + f[m] : f[m];
+              }
+            }
+          }
+        } else
         if (ok) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -1011,9 +1087,26 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
     if (p3_active) {
       const float* xr = x_t + ci3 * TS + 4;
       for (int q = q_begin; q < q_end; q += 4) {
-        const float4 xm = *reinterpret_cast<const float4*>(xr + q);
-        float x6[6] = {0.f, xm.x, xm.y, xm.z, xm.w, 0.f};
-        if constexpr (K == 3) { x6[0] = xr[q - 1]; x6[5] = xr[q + 4]; }
+        float4 xm;
+        float x6[6];
+        if constexpr (UP2) {   // x_up[q - 1 .. q + 4] = x[q/2 - 1], x[q/2] (x2), x[q/2 + 1] (x2), x[q/2 + 2]
+          const float* hr = xr + (q >> 1);
+          const float h0 = hr[0], h1 = hr[1];
+          x6[0] = hr[-1]; x6[1] = h0; x6[2] = h0; x6[3] = h1; x6[4] = h1; x6[5] = hr[2];
+          xm = make_float4(h0, h0, h1, h1);
+        } else {
+          xm = *reinterpret_cast<const float4*>(xr + q);
+          x6[0] = 0.f; x6[1] = xm.x; x6[2] = xm.y; x6[3] = xm.z; x6[4] = xm.w; x6[5] = 0.f;
+          if constexpr (K >= 3) { x6[0] = xr[q - 1]; x6[5] = xr[q + 4]; }
+        }
+        if constexpr (DOWN2) {   // output positions m0 = q / 2, m0 + 1 read x[2m + k - 1] = x6[k], x6[k + 2]
+#pragma unroll
+          for (int co = 0; co < COUT; ++co) {
+            const float d0 = du_s[co * TS + 4 + (q >> 1)], d1 = du_s[co * TS + 5 + (q >> 1)];
+#pragma unroll
+            for (int k = 0; k < K; ++k) dwacc[co][k] = fmaf(d0, x6[k], fmaf(d1, x6[k + 2], dwacc[co][k]));
+          }
+        } else
 #pragma unroll
         for (int co = 0; co < COUT; ++co) {
           const float4 d4 = *reinterpret_cast<const float4*>(du_s + co * TS + 4 + q);
@@ -1082,7 +1175,8 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
   }
 }
 
-template <int COUT, int K, int P, int NT, bool EPI, bool BULK, bool RES = false, int NCI = 0>
+template <int COUT, int K, int P, int NT, bool EPI, bool BULK, bool RES = false, int NCI = 0, bool UP2 = false,
+          bool DOWN2 = false>
 static int launch_fused_tma(ConvBwdFusedArgs a, cudaStream_t st) {
   constexpr int TL = NT * P, TS = TL + 36, NW = NT / 32;
   const int cin = a.c1 + a.c2;
@@ -1093,7 +1187,7 @@ static int launch_fused_tma(ConvBwdFusedArgs a, cudaStream_t st) {
   size_t smem = sizeof(float) * ((size_t)2 * rows * TS + (NCI > 0 ? 0 : (size_t)COUT * cin * 4) + (size_t)COUT * cin * K +
                                  (RES ? (size_t)2 * COUT * cin : 0) + NW * 2 * COUT) + 16;
   if (smem > 220 * 1024) return -6;
-  auto kern = conv_bwd_fused_tma_kernel<COUT, K, P, NT, EPI, BULK, RES, NCI>;
+  auto kern = conv_bwd_fused_tma_kernel<COUT, K, P, NT, EPI, BULK, RES, NCI, UP2, DOWN2>;
   static int sm_count = 0;
   if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1205,7 +1299,7 @@ static int dispatch_fused(const ConvBwdFusedArgs& a, int cout, cudaStream_t st) 
     }
   }
   switch (cout) {
-    case 1: return launch_fused<1, K, 4, 1>(a, st);
+    case 1: return v4 ? launch_fused<1, K, 4, 4>(a, st) : launch_fused<1, K, 4, 1>(a, st);
     case 4: return v4 ? launch_fused<4, K, 4, 4>(a, st) : launch_fused<4, K, 4, 1>(a, st);
     case 8: return v4 ? launch_fused<8, K, 4, 4>(a, st) : launch_fused<8, K, 4, 1>(a, st);
     case 12: return launch_fused<12, K, 2, 1>(a, st);
@@ -2133,6 +2227,54 @@ DQ_API int dq_conv_bwd_fused(const float* dy, const float* u, const float* g, co
   if (K == 3) return dispatch_fused<3>(a, cout, st);
   if (K == 1) return dispatch_fused<1>(a, cout, st);
   return -2;
+}
+
+// Backward of Upsample = nearest x2 + Conv1d(k3, pad 1) (unet1d.py:93-96) in ONE pass: dy (R, cout, 2 Lh), x / dx
+// (R, cin, Lh) at half rate; dw (cout, cin, 3) and db accumulated; dx NULL = not needed, acc = accumulate into dx.
+// Returns 1 (nothing launched) if the shape is not covered: dq_upsample2x + dq_conv_bwd_fused + dq_fold2x instead.
+DQ_API int dq_upconv_bwd_fused(const float* dy, const float* x, const float* w, float* dx, int acc, float* dw, float* db,
+                               int cout, int cin, int R, int Lh, int rows_per_sample, void* stream) {
+  ConvBwdFusedArgs a{dy, nullptr, nullptr, nullptr, x, nullptr, w, nullptr, dx, nullptr, dw, db, nullptr, nullptr, cin, 0, R,
+                     2 * Lh, rows_per_sample, 0, 0, acc, 0, 0, 0, 0};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (R <= 0 || Lh <= 0) return 0;
+  if ((cin & 3) || cin > 64 || 2 * Lh < 128) return 1;
+  const bool al = (Lh % 4 == 0) && ((((size_t)dy | (size_t)x) & 15) == 0);
+  switch (cout) {
+    case 4: return al ? launch_fused_tma<4, 3, 4, 128, false, true, false, 0, true>(a, st)
+                      : launch_fused_tma<4, 3, 4, 128, false, false, false, 0, true>(a, st);
+    case 8: return al ? launch_fused_tma<8, 3, 2, 128, false, true, false, 0, true>(a, st)
+                      : launch_fused_tma<8, 3, 2, 128, false, false, false, 0, true>(a, st);
+    case 12: return al ? launch_fused_tma<12, 3, 2, 128, false, true, false, 0, true>(a, st)
+                       : launch_fused_tma<12, 3, 2, 128, false, false, false, 0, true>(a, st);
+    case 16: return al ? launch_fused_tma<16, 3, 2, 128, false, true, false, 0, true>(a, st)
+                       : launch_fused_tma<16, 3, 2, 128, false, false, false, 0, true>(a, st);
+    default: return 1;
+  }
+}
+
+// Backward of Downsample = Conv1d(k4, stride 2, pad 1) (unet1d.py:110) in ONE pass: dy (R, cout, L / 2), x / dx (R, cin, L),
+// w / dw (cout, cin, 4); dw and db accumulated; dx NULL = not needed, acc = accumulate into dx.  Returns 1 (nothing
+// launched) if the shape is not covered: dq_s2d + dq_down_w + dq_conv_bwd_fused + dq_d2s instead.
+DQ_API int dq_downconv_bwd_fused(const float* dy, const float* x, const float* w, float* dx, int acc, float* dw, float* db,
+                                 int cout, int cin, int R, int L, int rows_per_sample, void* stream) {
+  ConvBwdFusedArgs a{dy, nullptr, nullptr, nullptr, x, nullptr, w, nullptr, dx, nullptr, dw, db, nullptr, nullptr, cin, 0, R,
+                     L, rows_per_sample, 0, 0, acc, 0, 0, 0, 0};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (R <= 0 || L <= 0) return 0;
+  if ((cin & 3) || cin > 64 || (L & 1) || L < 128) return 1;
+  const bool al = (L % 8 == 0) && ((((size_t)dy | (size_t)x | (size_t)dx) & 15) == 0);
+  switch (cout) {
+    case 4: return al ? launch_fused_tma<4, 4, 4, 128, false, true, false, 0, false, true>(a, st)
+                      : launch_fused_tma<4, 4, 4, 128, false, false, false, 0, false, true>(a, st);
+    case 8: return al ? launch_fused_tma<8, 4, 2, 128, false, true, false, 0, false, true>(a, st)
+                      : launch_fused_tma<8, 4, 2, 128, false, false, false, 0, false, true>(a, st);
+    case 12: return al ? launch_fused_tma<12, 4, 2, 128, false, true, false, 0, false, true>(a, st)
+                       : launch_fused_tma<12, 4, 2, 128, false, false, false, 0, false, true>(a, st);
+    case 16: return al ? launch_fused_tma<16, 4, 2, 128, false, true, false, 0, false, true>(a, st)
+                       : launch_fused_tma<16, 4, 2, 128, false, false, false, 0, false, true>(a, st);
+    default: return 1;
+  }
 }
 
 // dq_conv_bwd_fused (K = 3, with epilogue) plus the backward of ResnetBlock.res_conv, a 1x1 convolution over the same

@@ -34,6 +34,8 @@ _SIGS = {
     "dq_initconv_bwd": ("pppp" + "i" + "ppppp" + "iiii" + "s", 2),
     "dq_resblock_fwd": ("pipippppipppppppppiiiis", 1),
     "dq_sample_dot": ("ppppilis", 1),
+    "dq_upconv_bwd_fused": ("ppppippiiiiis", 1),
+    "dq_downconv_bwd_fused": ("ppppippiiiiis", 1),
     "dq_upsample2x": ("ppls", 1),
     "dq_fold2x": ("pplis", 1),
     "dq_s2d": ("ppiiis", 1),

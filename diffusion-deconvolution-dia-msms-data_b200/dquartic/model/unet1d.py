@@ -484,6 +484,13 @@ class UNet1d(nn.Module):
         """Backward of Upsample = nearest x2 + Conv1d(k3) (unet1d.py:93-96) through the fused stride-1 kernel: the
         upsampled input is rebuilt (never saved), d x_up is folded back pairwise."""
         R, c, Lh = x.shape
+        if not getattr(self, "_force_unfused_upconv", False):   # (test switch: the three-pass composition below)
+            acc = 1 if (need_dx and dx is not None) else 0
+            out = (dx if dx is not None else self._empty(R, c, Lh)) if need_dx else None
+            rc = N.call("dq_upconv_bwd_fused", du, x, self._w(wname), out, acc, self._gw(wname),
+                        self._gw(bname) if bname else None, du.shape[1], c, R, Lh, rps, allow=(1,))
+            if rc == 0:
+                return out
         xup = self._empty(R, c, 2 * Lh)
         N.call("dq_upsample2x", x, xup, x.numel())
         dxup, _ = self._conv_bwd_fused(du, None, None, None, ACT_NONE, xup, None, wname, bname, 3, need_dx1=need_dx, rps=rps)
@@ -501,6 +508,13 @@ class UNet1d(nn.Module):
         R, c, L = x.shape
         cout = du.shape[1]
         Lh = L // 2
+        if not getattr(self, "_force_unfused_downconv", False):   # (test switch: the re-indexing composition below)
+            acc = 1 if (need_dx and dx is not None) else 0
+            out = (dx if dx is not None else self._empty(R, c, L)) if need_dx else None
+            rc = N.call("dq_downconv_bwd_fused", du, x, self._w(wname), out, acc, self._gw(wname),
+                        self._gw(bname) if bname else None, cout, c, R, L, rps, allow=(1,))
+            if rc == 0:
+                return out
         xs = self._empty(R, 2 * c, Lh)
         N.call("dq_s2d", x, xs, R, c, L)
         w3 = self._empty(cout, 2 * c, 3)

@@ -86,7 +86,18 @@ int dq_conv_bwd_fused_res(const float* dy, const float* u, const float* g, const
  * space-to-depth x (R,C,L) -> (R,2C,L/2) [even samples | odd samples] and back; k4 weights (co,ci,4) <-> k3 weights
  * (co,2ci,3) (dir 0: pack, dir 1: w4 += unpack(w3)). */
 int dq_upsample2x(const float* x, float* y, long n, void* stream);
+/* Backward of Upsample = nearest x2 + Conv1d(k3, pad 1) (unet1d.py:93-96) in one pass: dy (R, cout, 2 Lh); x and dx
+ * (R, cin, Lh) at half rate - the upsampled tensor and its gradient never exist; dw (cout, cin, 3) / db accumulated; dx
+ * NULL = not needed, acc = accumulate into dx.  Returns 1 (nothing launched) if the shape is not covered: compose from
+ * dq_upsample2x + dq_conv_bwd_fused + dq_fold2x instead. */
+int dq_upconv_bwd_fused(const float* dy, const float* x, const float* w, float* dx, int acc, float* dw, float* db,
+                        int cout, int cin, int R, int Lh, int rows_per_sample, void* stream);
 int dq_fold2x(const float* d, float* dx, long n, int acc, void* stream);
+/* Backward of Downsample = Conv1d(k4, stride 2, pad 1) (unet1d.py:110) in one pass: dy (R, cout, L / 2); x and dx
+ * (R, cin, L); w / dw (cout, cin, 4); dw / db accumulated; dx NULL = not needed, acc = accumulate into dx.  Returns 1
+ * (nothing launched) if the shape is not covered: compose from dq_s2d + dq_down_w + dq_conv_bwd_fused + dq_d2s instead. */
+int dq_downconv_bwd_fused(const float* dy, const float* x, const float* w, float* dx, int acc, float* dw, float* db,
+                          int cout, int cin, int R, int L, int rows_per_sample, void* stream);
 int dq_s2d(const float* x, float* y, int R, int C, int L, void* stream);
 int dq_d2s(const float* d, float* dx, int R, int C, int L, int acc, void* stream);
 int dq_down_w(float* w4, float* w3, int co, int ci, int dir, void* stream);

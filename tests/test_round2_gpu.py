@@ -307,3 +307,60 @@ def test_tcgen05_linear_attention_backward_matches_mma_sync_kernel(C, L, pre):
     assert rel_err(dx, ref["dx"]) < 5e-3
     for k in names:
         assert rel_err(got[k], ref[k]) < 5e-3, k
+
+
+@pytest.mark.parametrize("j,Lh", [(0, 625), (1, 1250), (2, 320), (3, 100), (4, 2500), (5, 1284)])
+def test_upsample_backward_one_pass_matches_three_pass_composition(j, Lh):
+    """dq_upconv_bwd_fused (half-rate rows staged, pairs folded in registers) against dq_upsample2x + dq_conv_bwd_fused +
+    dq_fold2x: backward of Upsample = nearest x2 + Conv1d k3 (reference unet1d.py:93-96) at every channel pair of the up
+    path, with 16-byte aligned and unaligned rows, ragged last tiles, accumulation into dx and dx not needed."""
+    net, _ = make_net(seed=3)
+    net._ensure_grads()
+    wname, bname = f"ups.{j}.3.1.weight", f"ups.{j}.3.1.bias"
+    cout, cin, _ = net.specs[wname]
+    R = 5
+    g = torch.Generator(device="cuda").manual_seed(100 + j)
+    x = torch.randn(R, cin, Lh, device="cuda", generator=g)
+    du = torch.randn(R, cout, 2 * Lh, device="cuda", generator=g)
+    base = torch.randn(R, cin, Lh, device="cuda", generator=g)
+    res = []
+    for unfused in (True, False):
+        net._force_unfused_upconv = unfused
+        net.zero_grad()
+        dx = net._upconv_bwd(du, x, wname, bname, True, None, 1)
+        dxa = net._upconv_bwd(du, x, wname, bname, True, base.clone(), 1)
+        none = net._upconv_bwd(du, x, wname, bname, False, None, 1)
+        assert none is None
+        torch.cuda.synchronize()
+        res.append((dx.clone(), dxa.clone(), net._gw(wname).clone(), net._gw(bname).clone()))
+    for a, b, what in zip(res[0], res[1], ("dx", "dx accumulated", "dW", "db")):
+        assert rel_err(b, a) < 2e-5, (what, rel_err(b, a))
+
+
+@pytest.mark.parametrize("i,L", [(0, 1250), (1, 2500), (2, 640), (3, 200), (4, 5000), (5, 1284)])
+def test_downsample_backward_one_pass_matches_reindexing_composition(i, L):
+    """dq_downconv_bwd_fused (half-rate dy rows staged, k4 / stride-2 taps resolved in place) against dq_s2d + dq_down_w +
+    dq_conv_bwd_fused + dq_d2s: backward of Downsample = Conv1d(k4, s2, p1) (reference unet1d.py:110) at every channel pair
+    of the down path, aligned and unaligned rows, ragged last tiles, accumulation into dx and dx not needed."""
+    net, _ = make_net(seed=4)
+    net._ensure_grads()
+    wname, bname = f"downs.{i}.3.weight", f"downs.{i}.3.bias"
+    cout, cin, k = net.specs[wname]
+    assert k == 4
+    R = 5
+    g = torch.Generator(device="cuda").manual_seed(200 + i)
+    x = torch.randn(R, cin, L, device="cuda", generator=g)
+    du = torch.randn(R, cout, L // 2, device="cuda", generator=g)
+    base = torch.randn(R, cin, L, device="cuda", generator=g)
+    res = []
+    for unfused in (True, False):
+        net._force_unfused_downconv = unfused
+        net.zero_grad()
+        dx = net._downconv_bwd(du, x, wname, bname, True, None, 1)
+        dxa = net._downconv_bwd(du, x, wname, bname, True, base.clone(), 1)
+        none = net._downconv_bwd(du, x, wname, bname, False, None, 1)
+        assert none is None
+        torch.cuda.synchronize()
+        res.append((dx.clone(), dxa.clone(), net._gw(wname).clone(), net._gw(bname).clone()))
+    for a, b, what in zip(res[0], res[1], ("dx", "dx accumulated", "dW", "db")):
+        assert rel_err(b, a) < 2e-5, (what, rel_err(b, a))
