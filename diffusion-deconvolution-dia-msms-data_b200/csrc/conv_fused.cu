@@ -476,6 +476,13 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
   float* dwres_s = wres_s + (RES ? COUT * cin : 0);      // RES: COUT * cin
   float* red = dwres_s + (RES ? COUT * cin : 0);         // NW * 2 * COUT
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + NW * 2 * COUT);
+  // MMA variant: the identity-skip gradient (dadd) and the destination's old contents (acc1) of the tile are copied
+  // into shared memory during phase 1 ([c1][TS] each, position p at index p + 4): read from global memory in the
+  // phase-2 epilogue they were its long-scoreboard stall (ncu: block1 backward took 2x block2 at 12 channels)
+  float* add_s = reinterpret_cast<float*>(bars + 2);
+  constexpr bool STG = MMA && !RES;   // (the res_conv variant has neither dadd nor an accumulating destination)
+  const bool st_add = STG && a.dadd != nullptr && a.dx1 != nullptr, st_acc = STG && a.acc1 != 0 && a.dx1 != nullptr;
+  float* acc_s = add_s + (st_add ? a.c1 * TS : 0);
   const int tid = threadIdx.x;
   const uint32_t bar0 = cf_smem_u32(bars), bar1 = bar0 + 8;
 
@@ -580,6 +587,33 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
       }
     }
   };
+  // staged copies of a tile's dadd / old-dx1 rows: issued one tile ahead (after the end-of-tile barrier, before the stage
+  // prefetch) and committed as a cp.async group of their own, so that waiting for them (before phase 2 of their tile)
+  // never waits for the younger, uncommitted stage copies of the unaligned-row pipeline
+  auto issue_add = [&](int tile) {
+    if constexpr (STG) {
+      if (st_add || st_acc) {   // CTA-uniform
+        const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
+        const int wv = min(TL, a.L - tl0);
+        const int nrow = a.c1 * ((st_add ? 1 : 0) + (st_acc ? 1 : 0));
+        for (int row = tid >> 5; row < nrow; row += NW) {
+          const bool second = row >= a.c1;
+          const int ci = second ? row - a.c1 : row;
+          const float* src = ((st_add && !second) ? a.dadd : a.dx1) + ((size_t)r * a.c1 + ci) * a.L + tl0;
+          const uint32_t dst = cf_smem_u32(add_s + row * TS + 4);
+          if (BULK && (wv & 3) == 0 && (reinterpret_cast<size_t>(src) & 15) == 0) {
+            for (int e = (tid & 31) * 4; e < wv; e += 128)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 4u * (uint32_t)e), "l"(src + e) : "memory");
+          } else {
+            for (int e = tid & 31; e < wv; e += 32)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * (uint32_t)e), "l"(src + e) : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+    }
+  };
+  if (n_tiles > 0) issue_add(t_begin);
   if (n_tiles > 0) issue(t_begin, 0);
   if (n_tiles > 1) issue(t_begin + 1, 1);
 
@@ -843,6 +877,9 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
       if (tl0 == 0) x_t[tid * TS + 3] = 0.f;
       if (a.L <= tl0 + TL) x_t[tid * TS + (UP2 ? ((a.L - tl0) >> 1) : (a.L - tl0)) + 4] = 0.f;
     }
+    if constexpr (STG) {
+      if (st_add || st_acc) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncthreads();
 
     // ---------------------------------------------------------------- phase 2: dx for the thread's positions
@@ -851,16 +888,17 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
         // warp w: slabs of 16 positions w, w + NW, ..; D[pos][ci] = sum_k A_k[pos][co] W_k[co][ci] (+ dyo wres)
         // destination rows of this thread's channel pairs (ci = 8nt + 2ft, +1), fixed for the whole tile
         float* dstp[NCI];
-        const float* addp[NCI];
+        const float* addp[NCI];   // shared-memory copies of the tile (dadd rows, then the old dx1 rows)
+        const float* oldp[NCI];
         bool accp[NCI];
 #pragma unroll
         for (int nt = 0; nt < NCI; ++nt) {
           const int ci = 8 * nt + 2 * ft;
-          dstp[nt] = nullptr; addp[nt] = nullptr; accp[nt] = false;
+          dstp[nt] = nullptr; addp[nt] = nullptr; oldp[nt] = nullptr; accp[nt] = false;
           if (ci < a.c1) {
             if (a.dx1) dstp[nt] = a.dx1 + ((size_t)r * a.c1 + ci) * a.L + tl0 + fg;
-            if (a.dadd) addp[nt] = a.dadd + ((size_t)r * a.c1 + ci) * a.L + tl0 + fg;
-            accp[nt] = a.acc1 != 0;
+            if (st_add) addp[nt] = add_s + ci * TS + 4 + fg;
+            if (st_acc) oldp[nt] = acc_s + ci * TS + 4 + fg;
           } else if (ci < cin) {
             if (a.dx2) dstp[nt] = a.dx2 + ((size_t)r * a.c2 + (ci - a.c1)) * a.L + tl0 + fg;
             accp[nt] = a.acc2 != 0;
@@ -900,13 +938,19 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
             if (!dstp[nt]) continue;   // warp-uniform per nt only when c1 is a multiple of 8; divergence is harmless
             float* q0 = dstp[nt] + p0;
             float* q1 = q0 + a.L;
-            if (addp[nt] || accp[nt]) {
+            if (addp[nt] || oldp[nt] || accp[nt]) {
               float e[4] = {0.f, 0.f, 0.f, 0.f};
               if (addp[nt]) {
                 const float* z0 = addp[nt] + p0;
-                const float* z1 = z0 + a.L;
-                if (ok0) { e[0] += __ldg(z0); e[1] += __ldg(z1); }
-                if (ok1) { e[2] += __ldg(z0 + 8); e[3] += __ldg(z1 + 8); }
+                const float* z1 = z0 + TS;
+                if (ok0) { e[0] += z0[0]; e[1] += z1[0]; }
+                if (ok1) { e[2] += z0[8]; e[3] += z1[8]; }
+              }
+              if (oldp[nt]) {
+                const float* z0 = oldp[nt] + p0;
+                const float* z1 = z0 + TS;
+                if (ok0) { e[0] += z0[0]; e[1] += z1[0]; }
+                if (ok1) { e[2] += z0[8]; e[3] += z1[8]; }
               }
               if (accp[nt]) {
                 if (ok0) { e[0] += q0[0]; e[1] += q1[0]; }
@@ -1126,6 +1170,7 @@ __global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs
       }
     }
     __syncthreads();   // everyone is done with stage s
+    if (it + 1 < n_tiles) issue_add(tile + 1);
     if (it + 2 < n_tiles) issue(tile + 2, s);
   }
 
@@ -1186,6 +1231,8 @@ static int launch_fused_tma(ConvBwdFusedArgs a, cudaStream_t st) {
   a.al8 = ((((size_t)a.dy | (size_t)a.u | (size_t)a.x1 | (size_t)a.x2 | (size_t)a.dyo) & 7) == 0) ? 1 : 0;
   size_t smem = sizeof(float) * ((size_t)2 * rows * TS + (NCI > 0 ? 0 : (size_t)COUT * cin * 4) + (size_t)COUT * cin * K +
                                  (RES ? (size_t)2 * COUT * cin : 0) + NW * 2 * COUT) + 16;
+  if (NCI > 0 && !RES && a.dx1)   // staged copies of dadd / the old dx1 tile (see the kernel)
+    smem += sizeof(float) * (size_t)a.c1 * TS * ((a.dadd ? 1 : 0) + (a.acc1 ? 1 : 0));
   if (smem > 220 * 1024) return -6;
   auto kern = conv_bwd_fused_tma_kernel<COUT, K, P, NT, EPI, BULK, RES, NCI, UP2, DOWN2>;
   static int sm_count = 0;
