@@ -499,15 +499,17 @@ def dominant_kernel_roofline(torch, N, net, dev, n_samples=64):
     ach_b = 2.0 * fl_f / (ms_b * 1e-3) / 1e12
     # exp count: 128 (k) + 128 (q) per position forward, recomputed in backward; MUFU.EX2 = 16 / clk / SM
     exp_floor_ms = lambda n_exp: n_exp * R * L / (148 * 16 * 1.965e9) * 1e3
-    main = {"kernel": f"dq_linattn_bwd (la_bwd_q + la_bwd_combine + la_bwd_kv), level 0 (C=4, L=40000), {n_samples} samples",
+    main = {"kernel": f"dq_linattn_bwd (la_bwd_q_tc [tcgen05 / TMEM] + la_bwd_combine + la_bwd_kv [mma.sync]), level 0 (C=4, L=40000), {n_samples} samples",
             "bound": "tensor", "achieved": ach_b, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach_b / pk["tensor"],
             # dram__bytes_read.sum + dram__bytes_write.sum of la_bwd_q + la_bwd_combine + la_bwd_kv at exactly this shape
-            # (C = 4, L = 40000, 64 samples), one `ncu --set full` capture: profiles/r1d_la_bwd64_ncu_full_summary.txt
-            "traffic": (11.232e9 if n_samples == 64 else None), "traffic_unit": "bytes per dq_linattn_bwd call",
+            # (C = 4, L = 40000, 64 samples), one `ncu --set full` capture: profiles/r2c_la_bwd64_ncu_full_summary.txt
+            # (5.603 + 0.056 + 5.576 GB; the round-1 kernels moved the same bytes)
+            "traffic": (11.235e9 if n_samples == 64 else None), "traffic_unit": "bytes per dq_linattn_bwd call",
             "ms_per_launch": ms_b, "peak_source": pk["src"],
             "note": "algorithmic FLOPs = the reference's 32x32 per-head bmm's; the kernels factor them through the C "
-                    "input channels (32xC products, ~1/4 of the MMA work at C=4, mma.sync TF32) and are bound by "
-                    "MUFU.EX2 + instruction issue, not by the tensor pipe or HBM: MUFU floor "
+                    "input channels (32xC products, ~1/4 of the MMA work at C=4; q path: tcgen05.mma kind::tf32 / f16 with TMEM "
+                    "score rings, k/v path: mma.sync TF32) and are bound by MUFU.EX2 + instruction issue + the small-MMA "
+                    "pipeline skeleton (DESIGN.md section 4), not by the tensor pipe or HBM: MUFU floor "
                     f"{exp_floor_ms(256):.2f} ms vs {ms_b:.2f} ms measured; HBM-algorithmic bytes "
                     f"{8 * C * 4 * R * L / 1e9:.2f} GB = {8 * C * 4 * R * L / 1e9 / (ms_b * 1e-3):.0f} GB/s"}
     others.append({"kernel": f"dq_linattn_fwd (la_stats + la_combine + la_out), level 0, {n_samples} samples", "bound": "tensor",
