@@ -440,6 +440,11 @@ DQ_API int dq_conv1d_fwd(const float* x1, int c1, const float* x2, int c2, const
     int rc = conv_fwd_tma_try(x1, c1, x2, c2, w, bias, cout, K, g, ss, ss_stride, act, res, u, y, R, Lout, rows_per_sample, up, st);
     if (rc != 0) return rc < 0 ? rc : 0;
   }
+  if (stride == 2 && K == 4 && pad == 1 && up == 1 && !in_ss && !x2 && !res && Lin == 2 * Lout) {
+    // Downsample (unet1d.py:110) through the same pipelined kernel (up = -2: stride-2 mode)
+    int rc = conv_fwd_tma_try(x1, c1, nullptr, 0, w, bias, cout, K, g, ss, ss_stride, act, nullptr, u, y, R, Lout, rows_per_sample, -2, st);
+    if (rc != 0) return rc < 0 ? rc : 0;
+  }
   switch (cout) {
     case 1: return dispatch_fwd_mode<1>(a, K, stride, up, st);
     case 4: return dispatch_fwd_mode<4>(a, K, stride, up, st);

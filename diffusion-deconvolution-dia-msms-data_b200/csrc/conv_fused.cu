@@ -1371,13 +1371,17 @@ struct ConvFwdTmaArgs {
 // UP2: the input is the nearest-x2 upsampling of half-length rows (Upsample, unet1d.py:93-96): the half-rate rows are staged
 // and x_up[q] = x_half[q >> 1] is resolved when the taps are read, so the upsampled tensor never exists.
 
-template <int COUT, int K, int P, int NT, bool BULK, bool UP2>
+// DN2: Downsample = Conv1d(k4, stride 2, pad 1) (unet1d.py:110): a.L is the OUTPUT length, the input rows are 2 a.L long;
+// a thread owns P output positions m and reads x[2m - 1 .. 2m + 2] per tap window from the staged full-rate rows
+// (row stride 2 TL + 8), single source, no residual.
+template <int COUT, int K, int P, int NT, bool BULK, bool UP2, bool DN2 = false>
 __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
   constexpr int TL = NT * P;
-  constexpr int TS = TL + 36;
+  constexpr int TS = DN2 ? 2 * TL + 8 : TL + 36;
   constexpr int H = (K - 1) / 2;
   static_assert(P == 1 || P == 2 || P == 4, "P");
   static_assert(COUT % 4 == 0, "COUT");
+  static_assert(!DN2 || (K == 4 && !UP2), "DN2: k4 s2");
   extern __shared__ float4 dyn_smem4[];
   const int cin = a.c1 + a.c2;
   const bool has_res = a.res != nullptr;
@@ -1404,7 +1408,8 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
   auto issue = [&](int tile, int s) {
     if (!BULK) {   // any alignment: 4-byte cp.async from every thread, arriving on the same mbarrier
       const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
-      const int Lx = UP2 ? a.L / 2 : a.L, x0 = UP2 ? tl0 / 2 : tl0, xw_ = UP2 ? TL / 2 : TL;   // staged input window
+      const int Lx = UP2 ? a.L / 2 : DN2 ? 2 * a.L : a.L, x0 = UP2 ? tl0 / 2 : DN2 ? 2 * tl0 : tl0,
+                xw_ = UP2 ? TL / 2 : DN2 ? 2 * TL : TL;   // staged input window
       const int l_lo = max(0, x0 - 4), l_hi = min(Lx, x0 + xw_ + 4);
       const int w = l_hi - l_lo, doff = l_lo - (x0 - 4);
       float* st = stage0 + s * stage_floats;
@@ -1423,7 +1428,8 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
     }
     if (tid < 32) {
       const int r = tile / a.tiles_per_row, tl0 = (tile - r * a.tiles_per_row) * TL;
-      const int Lx = UP2 ? a.L / 2 : a.L, x0 = UP2 ? tl0 / 2 : tl0, xw_ = UP2 ? TL / 2 : TL;
+      const int Lx = UP2 ? a.L / 2 : DN2 ? 2 * a.L : a.L, x0 = UP2 ? tl0 / 2 : DN2 ? 2 * tl0 : tl0,
+                xw_ = UP2 ? TL / 2 : DN2 ? 2 * TL : TL;
       const int l_lo = max(0, x0 - 4), l_hi = min(Lx, x0 + xw_ + 4);
       const uint32_t bytes = (uint32_t)(l_hi - l_lo) * 4u;
       const uint32_t bar = s ? bar1 : bar0;
@@ -1458,7 +1464,7 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
     if (H > 0) {   // zero padding at the two row ends (positions -1 and L)
       if (tid < cin) {
         if (tl0 == 0) x_t[tid * TS + 3] = 0.f;
-        if (a.L <= tl0 + TL) x_t[tid * TS + (UP2 ? (a.L - tl0) / 2 : a.L - tl0) + 4] = 0.f;
+        if (a.L <= tl0 + TL) x_t[tid * TS + (UP2 ? (a.L - tl0) / 2 : DN2 ? 2 * (a.L - tl0) : a.L - tl0) + 4] = 0.f;
       }
       if (tl0 == 0 || a.L <= tl0 + TL) __syncthreads();   // uniform per tile
     }
@@ -1471,7 +1477,22 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
       for (int c = 0; c < COUT; ++c) acc[i][c] = bias[c];
 #pragma unroll 2
     for (int ci = 0; ci < cin; ++ci) {
-      float xw[P + 2];
+      float xw[DN2 ? 2 * P + 2 : P + 2];
+      if constexpr (DN2) {   // xw[e] = x[2 m0 - 1 + e], m0 = this thread's first output position
+        const float* xb = x_t + ci * TS + 4 + 2 * P * tid;
+        xw[0] = xb[-1];
+        if constexpr (P >= 2) {
+#pragma unroll
+          for (int v = 0; v < P / 2; ++v) {
+            const float4 m = *reinterpret_cast<const float4*>(xb + 4 * v);
+            xw[4 * v + 1] = m.x; xw[4 * v + 2] = m.y; xw[4 * v + 3] = m.z; xw[4 * v + 4] = m.w;
+          }
+        } else {
+          const float2 m = *reinterpret_cast<const float2*>(xb);
+          xw[1] = m.x; xw[2] = m.y;
+        }
+        xw[2 * P + 1] = xb[2 * P];
+      }
       if constexpr (UP2) {
         // x_up[tl0 + P tid + i - 1] = x_half[(P tid + i - 1) >> 1]  (index -1 >> 1 = -1: the zeroed left neighbour)
         const float* xh = x_t + ci * TS + 4;
@@ -1484,7 +1505,7 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
         }
       }
       const float* xr = x_t + ci * TS + 4 + P * tid;
-      if constexpr (UP2) {
+      if constexpr (UP2 || DN2) {
       } else if constexpr (P == 4) { const float4 m = *reinterpret_cast<const float4*>(xr); xw[1] = m.x; xw[2] = m.y; xw[3] = m.z; xw[P] = m.w; }
       else if constexpr (P == 2) { const float2 m = *reinterpret_cast<const float2*>(xr); xw[1] = m.x; xw[P] = m.y; }
       else xw[1] = xr[0];
@@ -1497,7 +1518,7 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
           const float4 w4 = wp[c4];
 #pragma unroll
           for (int i = 0; i < P; ++i) {
-            const float xv = xw[i + 1 + k - H];
+            const float xv = DN2 ? xw[2 * i + k] : xw[i + 1 + k - H];
             cf_fma2(acc[i][4 * c4 + 0], acc[i][4 * c4 + 1], xv, w4.x, w4.y);
             cf_fma2(acc[i][4 * c4 + 2], acc[i][4 * c4 + 3], xv, w4.z, w4.w);
           }
@@ -1557,16 +1578,16 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
   }
 }
 
-template <int COUT, int K, int P, int NT, bool BULK, bool UP2>
+template <int COUT, int K, int P, int NT, bool BULK, bool UP2, bool DN2 = false>
 static int launch_fwd_tma(ConvFwdTmaArgs a, cudaStream_t st) {
-  constexpr int TL = NT * P, TS = TL + 36;
+  constexpr int TL = NT * P, TS = DN2 ? 2 * TL + 8 : TL + 36;
   const int cin = a.c1 + a.c2;
   const int rows = cin + (a.res ? COUT : 0);
   a.tiles_per_row = (a.L + TL - 1) / TL;
   a.total_tiles = a.tiles_per_row * a.R;
   size_t smem = sizeof(float) * ((size_t)2 * rows * TS + (size_t)cin * K * COUT) + 16;
   if (smem > 220 * 1024) return -6;
-  auto kern = conv_fwd_tma_kernel<COUT, K, P, NT, BULK, UP2>;
+  auto kern = conv_fwd_tma_kernel<COUT, K, P, NT, BULK, UP2, DN2>;
   static int sm_count = 0;
   if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1588,9 +1609,11 @@ int conv_fwd_tma_try(const float* x1, int c1, const float* x2, int c2, const flo
                      int L, int rows_per_sample, int up, cudaStream_t st) {
   static int mode = -1;   // DQ_CONV_FWD_NOTMA=1 forces the plain-load kernel (cross-check)
   if (mode < 0) { const char* e = getenv("DQ_CONV_FWD_NOTMA"); mode = (e && e[0] == '1') ? 1 : 0; }
-  if (mode == 1 || (K != 1 && K != 3) || L < 128 || c1 + c2 > 64) return 0;
+  if (mode == 1 || L < 128 || c1 + c2 > 64) return 0;
+  if (up == -2) { if (K != 4 || x2 || res) return 0; }   // Downsample: k4, stride 2, pad 1; L = output length
+  else if (K != 1 && K != 3) return 0;
   if (up == 2 && (K != 3 || x2 || res || (L & 1))) return 0;
-  const int Lx = up == 2 ? L / 2 : L;
+  const int Lx = up == 2 ? L / 2 : up == -2 ? 2 * L : L;
   const bool al = (L % 4 == 0) && (Lx % 4 == 0) && ((((size_t)x1 | (size_t)x2 | (size_t)res | (size_t)u | (size_t)y) & 15) == 0);
   ConvFwdTmaArgs a{x1, x2, w, bias, g, ss, res, u, y, c1, c2, R, L, rows_per_sample, ss_stride, act, 0, 0, 0};
   int rc;
@@ -1598,7 +1621,17 @@ int conv_fwd_tma_try(const float* x1, int c1, const float* x2, int c2, const flo
   case CO: rc = al ? launch_fwd_tma<CO, KK, PA, 128, true, false>(a, st) : launch_fwd_tma<CO, KK, PU, 128, false, false>(a, st); break;
 #define DQ_FWD_CASE_UP(CO, PA, PU) \
   case CO: rc = al ? launch_fwd_tma<CO, 3, PA, 128, true, true>(a, st) : launch_fwd_tma<CO, 3, PU, 128, false, true>(a, st); break;
-  if (up == 2) {
+#define DQ_FWD_CASE_DN(CO, PA) \
+  case CO: rc = al ? launch_fwd_tma<CO, 4, PA, 128, true, false, true>(a, st) : launch_fwd_tma<CO, 4, PA, 128, false, false, true>(a, st); break;
+  if (up == -2) {
+    switch (cout) {
+      DQ_FWD_CASE_DN(4, 4)
+      DQ_FWD_CASE_DN(8, 2)
+      DQ_FWD_CASE_DN(12, 2)
+      DQ_FWD_CASE_DN(16, 2)
+      default: return 0;
+    }
+  } else if (up == 2) {
     switch (cout) {
       DQ_FWD_CASE_UP(4, 4, 4)
       DQ_FWD_CASE_UP(8, 4, 2)
@@ -1625,6 +1658,7 @@ int conv_fwd_tma_try(const float* x1, int c1, const float* x2, int c2, const flo
   }
 #undef DQ_FWD_CASE
 #undef DQ_FWD_CASE_UP
+#undef DQ_FWD_CASE_DN
   return rc == 0 ? 1 : rc;
 }
 

@@ -364,3 +364,20 @@ def test_downsample_backward_one_pass_matches_reindexing_composition(i, L):
         res.append((dx.clone(), dxa.clone(), net._gw(wname).clone(), net._gw(bname).clone()))
     for a, b, what in zip(res[0], res[1], ("dx", "dx accumulated", "dW", "db")):
         assert rel_err(b, a) < 2e-5, (what, rel_err(b, a))
+
+
+@pytest.mark.parametrize("i,L", [(0, 1250), (1, 2500), (2, 640), (3, 256), (4, 5000), (5, 1284), (0, 40000)])
+def test_downsample_forward_pipelined_kernel_vs_torch(i, L):
+    """Downsample = Conv1d(k4, stride 2, pad 1) (reference unet1d.py:110) through the bulk-copy pipelined forward kernel
+    (stride-2 mode) against torch's fp32 convolution: every channel pair of the down path, aligned / unaligned rows,
+    ragged last tiles."""
+    net, _ = make_net(seed=5)
+    wname, bname = f"downs.{i}.3.weight", f"downs.{i}.3.bias"
+    cout, cin, k = net.specs[wname]
+    R = 3
+    g = torch.Generator(device="cuda").manual_seed(300 + i)
+    x = torch.randn(R, cin, L, device="cuda", generator=g)
+    y, _ = net._conv_fwd(x, None, wname, bname, 4, 2, 1, 1, L // 2)
+    ref = torch.nn.functional.conv1d(x, net._w(wname).view(cout, cin, k), net._w(bname), stride=2, padding=1)
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) < 1e-5, rel_err(y, ref)
