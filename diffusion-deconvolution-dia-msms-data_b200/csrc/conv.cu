@@ -423,7 +423,7 @@ using namespace dq;
 namespace dq {
 int conv_fwd_tma_try(const float* x1, int c1, const float* x2, int c2, const float* w, const float* bias, int cout, int K,
                      const float* g, const float* ss, int ss_stride, int act, const float* res, float* u, float* y, int R,
-                     int L, int rows_per_sample, int up, cudaStream_t st);
+                     int L, int rows_per_sample, int up, cudaStream_t st, const float* in_ss = nullptr, int in_ss_stride = 0);
 }
 
 // C-ABI ---------------------------------------------------------------------------------------------------------
@@ -435,9 +435,10 @@ DQ_API int dq_conv1d_fwd(const float* x1, int c1, const float* x2, int c2, const
                 in_ss_stride, act};
   cudaStream_t st = (cudaStream_t)stream;
   if (R <= 0 || Lout <= 0) return 0;
-  if (stride == 1 && !in_ss && pad == (K - 1) / 2 && ((up == 1 && Lin == Lout) || (up == 2 && 2 * Lin == Lout))) {
+  if (stride == 1 && (!in_ss || K == 7) && pad == (K - 1) / 2 && ((up == 1 && Lin == Lout) || (up == 2 && 2 * Lin == Lout))) {
     // bulk-copy pipelined kernel (conv_fused.cu)
-    int rc = conv_fwd_tma_try(x1, c1, x2, c2, w, bias, cout, K, g, ss, ss_stride, act, res, u, y, R, Lout, rows_per_sample, up, st);
+    int rc = conv_fwd_tma_try(x1, c1, x2, c2, w, bias, cout, K, g, ss, ss_stride, act, res, u, y, R, Lout, rows_per_sample, up, st,
+                              in_ss, in_ss_stride);
     if (rc != 0) return rc < 0 ? rc : 0;
   }
   if (stride == 2 && K == 4 && pad == 1 && up == 1 && !in_ss && !x2 && !res && Lin == 2 * Lout) {

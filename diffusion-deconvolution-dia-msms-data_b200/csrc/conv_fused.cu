@@ -1367,6 +1367,10 @@ struct ConvFwdTmaArgs {
   const float* x1; const float* x2; const float* w; const float* bias; const float* g; const float* ss;
   const float* res; float* u; float* y;
   int c1, c2, R, L, rows_per_sample, ss_stride, act, tiles_per_row, total_tiles, tiles_per_cta;
+  // K = 7 (init_conv over cat(ConditionalScaleShift(cond), x), unet1d.py:1107-1117): source-1 channel c is
+  // x * (in_ss[c] + 1) + in_ss[c1 + c] per sample at existing positions (the zero padding stays zero)
+  const float* in_ss = nullptr;
+  int in_ss_stride = 0;
 };
 // UP2: the input is the nearest-x2 upsampling of half-length rows (Upsample, unet1d.py:93-96): the half-rate rows are staged
 // and x_up[q] = x_half[q >> 1] is resolved when the taps are read, so the upsampled tensor never exists.
@@ -1382,6 +1386,7 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
   static_assert(P == 1 || P == 2 || P == 4, "P");
   static_assert(COUT % 4 == 0, "COUT");
   static_assert(!DN2 || (K == 4 && !UP2), "DN2: k4 s2");
+  static_assert(K != 7 || (!UP2 && !DN2), "k7: plain stride-1 mode");
   extern __shared__ float4 dyn_smem4[];
   const int cin = a.c1 + a.c2;
   const bool has_res = a.res != nullptr;
@@ -1461,11 +1466,27 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
     const int sample = r / a.rows_per_sample;
     float* x_t = stage0 + s * stage_floats;
     cf_mbar_wait(s ? bar1 : bar0, (uint32_t)((it >> 1) & 1));
-    if (H > 0) {   // zero padding at the two row ends (positions -1 and L)
+    if (H > 0) {   // zero padding at the two row ends (positions -1 .. -H and L .. L + H - 1)
       if (tid < cin) {
-        if (tl0 == 0) x_t[tid * TS + 3] = 0.f;
-        if (a.L <= tl0 + TL) x_t[tid * TS + (UP2 ? (a.L - tl0) / 2 : DN2 ? 2 * (a.L - tl0) : a.L - tl0) + 4] = 0.f;
+#pragma unroll
+        for (int h = 0; h < (K == 7 ? 3 : 1); ++h) {
+          if (tl0 == 0) x_t[tid * TS + 3 - h] = 0.f;
+          if (a.L <= tl0 + TL) x_t[tid * TS + (UP2 ? (a.L - tl0) / 2 : DN2 ? 2 * (a.L - tl0) : a.L - tl0) + 4 + h] = 0.f;
+        }
       }
+      if constexpr (K == 7) {
+        if (a.in_ss) {   // ConditionalScaleShift on source 1, in place, existing positions of the window only
+          for (int ci = 0; ci < a.c1; ++ci) {
+            const float sc = a.in_ss[(size_t)sample * a.in_ss_stride + ci] + 1.f;
+            const float sh = a.in_ss[(size_t)sample * a.in_ss_stride + a.c1 + ci];
+            for (int j = tid; j < TL + 8; j += NT) {
+              const int l = tl0 - 4 + j;
+              if (l >= 0 && l < a.L) x_t[ci * TS + j] = fmaf(x_t[ci * TS + j], sc, sh);
+            }
+          }
+        }
+        __syncthreads();
+      } else
       if (tl0 == 0 || a.L <= tl0 + TL) __syncthreads();   // uniform per tile
     }
     const int l = tl0 + P * tid;
@@ -1477,7 +1498,17 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
       for (int c = 0; c < COUT; ++c) acc[i][c] = bias[c];
 #pragma unroll 2
     for (int ci = 0; ci < cin; ++ci) {
-      float xw[DN2 ? 2 * P + 2 : P + 2];
+      float xw[DN2 ? 2 * P + 2 : K == 7 ? P + 6 : P + 2];
+      if constexpr (K == 7) {   // xw[e] = x[l - 3 + e]
+        const float* xb = x_t + ci * TS + 4 + P * tid;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { xw[e] = xb[e - 3]; xw[P + 3 + e] = xb[P + e]; }
+        if constexpr (P == 4) { const float4 m = *reinterpret_cast<const float4*>(xb); xw[3] = m.x; xw[4] = m.y; xw[5] = m.z; xw[6] = m.w; }
+        else {
+#pragma unroll
+          for (int e = 0; e < P; ++e) xw[3 + e] = xb[e];
+        }
+      }
       if constexpr (DN2) {   // xw[e] = x[2 m0 - 1 + e], m0 = this thread's first output position
         const float* xb = x_t + ci * TS + 4 + 2 * P * tid;
         xw[0] = xb[-1];
@@ -1505,7 +1536,7 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
         }
       }
       const float* xr = x_t + ci * TS + 4 + P * tid;
-      if constexpr (UP2 || DN2) {
+      if constexpr (UP2 || DN2 || K == 7) {
       } else if constexpr (P == 4) { const float4 m = *reinterpret_cast<const float4*>(xr); xw[1] = m.x; xw[2] = m.y; xw[3] = m.z; xw[P] = m.w; }
       else if constexpr (P == 2) { const float2 m = *reinterpret_cast<const float2*>(xr); xw[1] = m.x; xw[P] = m.y; }
       else xw[1] = xr[0];
@@ -1518,7 +1549,7 @@ __global__ void __launch_bounds__(NT) conv_fwd_tma_kernel(ConvFwdTmaArgs a) {
           const float4 w4 = wp[c4];
 #pragma unroll
           for (int i = 0; i < P; ++i) {
-            const float xv = DN2 ? xw[2 * i + k] : xw[i + 1 + k - H];
+            const float xv = DN2 ? xw[2 * i + k] : K == 7 ? xw[i + k] : xw[i + 1 + k - H];
             cf_fma2(acc[i][4 * c4 + 0], acc[i][4 * c4 + 1], xv, w4.x, w4.y);
             cf_fma2(acc[i][4 * c4 + 2], acc[i][4 * c4 + 3], xv, w4.z, w4.w);
           }
@@ -1606,16 +1637,19 @@ static int launch_fwd_tma(ConvFwdTmaArgs a, cudaStream_t st) {
 // L / 2 columns (nearest-x2 upsampling folded into the tap reads), K == 3, single source, no residual.
 int conv_fwd_tma_try(const float* x1, int c1, const float* x2, int c2, const float* w, const float* bias, int cout, int K,
                      const float* g, const float* ss, int ss_stride, int act, const float* res, float* u, float* y, int R,
-                     int L, int rows_per_sample, int up, cudaStream_t st) {
+                     int L, int rows_per_sample, int up, cudaStream_t st, const float* in_ss, int in_ss_stride) {
   static int mode = -1;   // DQ_CONV_FWD_NOTMA=1 forces the plain-load kernel (cross-check)
   if (mode < 0) { const char* e = getenv("DQ_CONV_FWD_NOTMA"); mode = (e && e[0] == '1') ? 1 : 0; }
   if (mode == 1 || L < 128 || c1 + c2 > 64) return 0;
   if (up == -2) { if (K != 4 || x2 || res) return 0; }   // Downsample: k4, stride 2, pad 1; L = output length
+  else if (K == 7) { if (up != 1 || res || (cout != 4 && cout != 8)) return 0; }
   else if (K != 1 && K != 3) return 0;
+  if (in_ss && K != 7) return 0;
   if (up == 2 && (K != 3 || x2 || res || (L & 1))) return 0;
   const int Lx = up == 2 ? L / 2 : up == -2 ? 2 * L : L;
   const bool al = (L % 4 == 0) && (Lx % 4 == 0) && ((((size_t)x1 | (size_t)x2 | (size_t)res | (size_t)u | (size_t)y) & 15) == 0);
   ConvFwdTmaArgs a{x1, x2, w, bias, g, ss, res, u, y, c1, c2, R, L, rows_per_sample, ss_stride, act, 0, 0, 0};
+  a.in_ss = in_ss; a.in_ss_stride = in_ss_stride;
   int rc;
 #define DQ_FWD_CASE(CO, KK, PA, PU) \
   case CO: rc = al ? launch_fwd_tma<CO, KK, PA, 128, true, false>(a, st) : launch_fwd_tma<CO, KK, PU, 128, false, false>(a, st); break;
@@ -1623,7 +1657,13 @@ int conv_fwd_tma_try(const float* x1, int c1, const float* x2, int c2, const flo
   case CO: rc = al ? launch_fwd_tma<CO, 3, PA, 128, true, true>(a, st) : launch_fwd_tma<CO, 3, PU, 128, false, true>(a, st); break;
 #define DQ_FWD_CASE_DN(CO, PA) \
   case CO: rc = al ? launch_fwd_tma<CO, 4, PA, 128, true, false, true>(a, st) : launch_fwd_tma<CO, 4, PA, 128, false, false, true>(a, st); break;
-  if (up == -2) {
+  if (K == 7) {
+    switch (cout) {
+      DQ_FWD_CASE(4, 7, 4, 4)
+      DQ_FWD_CASE(8, 7, 4, 2)
+      default: return 0;
+    }
+  } else if (up == -2) {
     switch (cout) {
       DQ_FWD_CASE_DN(4, 4)
       DQ_FWD_CASE_DN(8, 2)

@@ -381,3 +381,26 @@ def test_downsample_forward_pipelined_kernel_vs_torch(i, L):
     ref = torch.nn.functional.conv1d(x, net._w(wname).view(cout, cin, k), net._w(bname), stride=2, padding=1)
     assert y.shape == ref.shape
     assert rel_err(y, ref) < 1e-5, rel_err(y, ref)
+
+
+@pytest.mark.parametrize("L,rt", [(40000, 3), (1250, 2), (333, 4), (128, 1)])
+def test_init_conv_forward_pipelined_kernel_vs_torch(L, rt):
+    """init_conv = Conv1d(2 -> dim, k7, pad 3) over cat(ConditionalScaleShift(cond), x) (reference unet1d.py:1107-1117,
+    677-678) through the pipelined forward kernel (k7 mode, the per-sample scale / shift applied to the staged rows at
+    existing positions only) against torch's fp32 ops."""
+    net, _ = make_net(seed=6)
+    b = 2
+    R = b * rt
+    net._time_path_fwd(torch.tensor([3, 700], device="cuda"), b, False)
+    g = torch.Generator(device="cuda").manual_seed(17)
+    net._SS.copy_(torch.randn(net._SS.shape, device="cuda", generator=g) * 0.5)
+    ico = net.ss_off["init_cond_proj.to_scale_shift.1"]
+    cond = torch.randn(R, 1, L, device="cuda", generator=g)
+    x = torch.randn(R, 1, L, device="cuda", generator=g)
+    y, _ = net._conv_fwd(cond, x, "init_conv.weight", "init_conv.bias", 7, 1, 3, 1, L, in_ss=ico, rps=rt)
+    cout = net.specs["init_conv.weight"][0]
+    sc = net._SS[:, ico].repeat_interleave(rt).view(R, 1, 1) + 1.0
+    sh = net._SS[:, ico + 1].repeat_interleave(rt).view(R, 1, 1)
+    ref = torch.nn.functional.conv1d(torch.cat([cond * sc + sh, x], 1), net._w("init_conv.weight").view(cout, 2, 7),
+                                     net._w("init_conv.bias"), padding=3)
+    assert rel_err(y, ref) < 1e-5, rel_err(y, ref)
