@@ -166,3 +166,29 @@ def test_reference_vendoring_recipe_runs_where_the_reference_is():
     if os.path.isdir("/root/reference/dquartic"):
         for rel in ("dquartic/model/model.py", "dquartic/model/unet1d.py", "rotary_embedding_torch.py"):
             assert os.path.exists(os.path.join(root, "oracle", "_ref", rel))
+
+
+def test_deferred_parameter_gathers_are_awaited_before_the_parameters_are_read():
+    """`FusedAdamW.step(defer_gather=True)` leaves the parameter all-gathers in flight; `UNet1d.sync_params` (called by
+    `flat_params`, `state_dict`, the bf16 operand refresh and deepcopy) must wait for every one of them exactly once."""
+    from dquartic.model.unet1d import UNet1d
+
+    class _Work:
+        def __init__(self):
+            self.waited = 0
+
+        def wait(self):
+            self.waited += 1
+
+    class _Shell:   # the two attributes the methods touch, without building a network
+        sync_params = UNet1d.sync_params
+        flat_params = UNet1d.flat_params
+
+    sh = _Shell()
+    sh._flat = torch.zeros(3)
+    works = [_Work(), _Work()]
+    sh.__dict__["_pending_param_works"] = list(works)
+    assert sh.flat_params() is sh._flat
+    assert [w.waited for w in works] == [1, 1] and sh.__dict__["_pending_param_works"] == []
+    sh.sync_params()                      # nothing pending: no second wait
+    assert [w.waited for w in works] == [1, 1]
