@@ -43,6 +43,12 @@ struct TC {
   static constexpr int PS = 2 + CP;                                   // partial record: m, s, M[CP]
   static constexpr int YS = C;                                        // row stride of per-head [pos][c] partial tiles (only c < C stored)
 };
+#ifndef LA_KV_ASYNC_MAXC
+#define LA_KV_ASYNC_MAXC 4  // k / v backward: epilogue inputs and the next x tile prefetched by cp.async up to this C
+#endif
+#ifndef LA_OCC8
+#define LA_OCC8 4  // resident CTAs per SM asked of the C = 8 backward kernels
+#endif
 #ifndef LA_OCC4
 #define LA_OCC4 5  // resident CTAs per SM asked of the C = 4 backward kernels
 #endif
@@ -625,7 +631,7 @@ __global__ void __launch_bounds__(128) la_out_kernel(LAArgs a) {
 // Reductions over positions (Gq = Qs^T dY, dWq = dQr^T Xn) read Qs / dQr back from warp-private shared tiles in
 // the transposed role.
 template <int C>
-__global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la_bwd_q_kernel(LAArgs a) {
+__global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? LA_OCC8 : 1))) la_bwd_q_kernel(LAArgs a) {
   using T = TC<C>;
   extern __shared__ float4 dyn_smem4[];
   // C = 4: ONE [pos][8] tile with xn and dy interleaved (xn0, dy0, xn1, dy1, ..): a single A fragment then carries xn
@@ -947,7 +953,7 @@ __global__ void __launch_bounds__(128) la_bwd_combine_kernel(LAArgs a, int rows_
 
 // ------------------------------------------------------------------------------------------- backward: k path
 template <int C>
-__global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la_bwd_kv_kernel(LAArgs a) {
+__global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? LA_OCC8 : 1))) la_bwd_kv_kernel(LAArgs a) {
   using T = TC<C>;
   extern __shared__ float4 dyn_smem4[];
   float* xn_s = reinterpret_cast<float*>(dyn_smem4);   // TA<C>::SIZE (natural A-operand layout)
@@ -956,7 +962,7 @@ __global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? 4 : 1))) la
   float* scr = yp_s + 4 * SP * T::YS;                  // 4 warps * 16 * RS
   float* inv_s = scr + 4 * 16 * RS;                    // SP
   float* acc_s = inv_s + SP;                           // C (d g_pre)
-  constexpr bool kAsync = (C == 4);                    // prefetch through shared memory (see la_bwd_q_kernel)
+  constexpr bool kAsync = (C <= LA_KV_ASYNC_MAXC);     // prefetch through shared memory (see la_bwd_q_kernel)
   float* pf_s = acc_s + C;                             // kAsync: 4 * C * SP: x (two alternating slots), dxnq, dres
   const int lane = threadIdx.x & 31, h = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int r = blockIdx.y;
@@ -1209,7 +1215,7 @@ static int la_bwd(const LAArgs& a, cudaStream_t st) {
   if (kv_tc < 0) { const char* e = getenv("DQ_LA_KV_TC"); kv_tc = (e && e[0] == '1') ? 1 : 0; }
   if (la_tc_enabled() && kv_tc && (C == 4 || C == 8)) return la_bwd_kv_tc(a, C, st);   // hybrid tcgen05 + mma.sync f16 kernel
   {
-    size_t smem = sizeof(float) * (TA<C>::SIZE + C * XT + 4 * SP * T::YS + 4 * 16 * RS + SP + C + (C == 4 ? 4 * C * SP : 0));
+    size_t smem = sizeof(float) * (TA<C>::SIZE + C * XT + 4 * SP * T::YS + 4 * 16 * RS + SP + C + (C <= LA_KV_ASYNC_MAXC ? 4 * C * SP : 0));
     cudaFuncSetAttribute(la_bwd_kv_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     la_bwd_kv_kernel<C><<<grid, 128, smem, st>>>(a);
     DQ_LAUNCH_CHECK();
