@@ -25,6 +25,12 @@
 #include "linattn_args.cuh"
 #include "linattn_tc.cuh"
 
+#ifndef LA_AUX_SETS
+#define LA_AUX_SETS 1
+#endif
+#ifndef LA_AUX_SETS8
+#define LA_AUX_SETS8 2
+#endif
 namespace dq {
 namespace tc {
 
@@ -69,14 +75,15 @@ struct BQ {
   static constexpr int oBAR = oDR + 2 * TILE;
   static constexpr int NBAR = 48;
   static constexpr int SMEM = oBAR + NBAR * 8 + 16 + 128;   // barriers, TMEM address slot, per-warp wait record
+  // staging / draining warp sets (tile t belongs to set t % AUX).  Measured (level shapes, 16 samples, whole backward):
+  // C = 4: 1 set (24 warps, 80 registers) 3.57 ms vs 2 sets (28 warps, 72 registers, spills) 3.77 ms; C = 8, where a
+  // set stages twice the channels per tile and was the pipeline's critical path: 1.57 -> 1.43 ms (L = 10000),
+  // 0.85 -> 0.80 ms (L = 5000) with 2 sets; C = 12: no difference.
+  static constexpr int AUX = (C == 8) ? LA_AUX_SETS8 : LA_AUX_SETS;
+  static constexpr int MMAW0 = 16 + 4 * AUX;             // first MMA-issuing warp
+  static constexpr int THREADS = (MMAW0 + 4) * 32;       // 16 compute + 4 AUX staging / draining + 4 MMA warps
 };
 constexpr int NREG = 5;       // slots of the TMEM score rings
-#ifndef LA_AUX_SETS
-#define LA_AUX_SETS 1   // measured: 1 set (24 warps, 80 registers) 1.92 ms vs 2 sets (28 warps, 72 registers, spills) 2.02 ms
-#endif
-constexpr int kAuxSets = LA_AUX_SETS;                 // staging / draining warp sets (tile t belongs to set t % kAuxSets)
-constexpr int kMmaWarp0 = 16 + 4 * kAuxSets;
-constexpr int kThreadsQ = (kMmaWarp0 + 4) * 32;       // 16 compute + 4 kAuxSets staging / draining + 4 MMA warps
 // mbarrier indices
 // The score-ring barriers are indexed by s % (2 NREG): the compute groups (and the two score-issuing warps) are NOT
 // ordered among each other, so with one barrier per slot a waiter could be two phases ahead of the barrier and its
@@ -86,7 +93,7 @@ constexpr int bS = 0, bLD = 10, bDONE = 20, bA = 24, bDXN = 28, bDXNFREE = 30, b
 constexpr uint32_t cQ = 0, cDQ = 160, cDR = 320, cDXN = 448, cGQ = 480, cDWQ = 496;
 
 template <int C>
-__global__ void __launch_bounds__(kThreadsQ, 1) la_bwd_q_tc_kernel(LAArgs a) {
+__global__ void __launch_bounds__(BQ<C>::THREADS, 1) la_bwd_q_tc_kernel(LAArgs a) {
   using K = BQ<C>;
   extern __shared__ __align__(16) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -107,10 +114,10 @@ __global__ void __launch_bounds__(kThreadsQ, 1) la_bwd_q_tc_kernel(LAArgs a) {
     for (int i = 0; i < K::NSTG; ++i) { mbar_init(BAR(bFULL + i), 4); mbar_init(BAR(bSFREE + i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kMmaWarp0) tmem_alloc(smem_u32(const_cast<const uint32_t*>(tslot)), 512);
+  if (warp == K::MMAW0) tmem_alloc(smem_u32(const_cast<const uint32_t*>(tslot)), 512);
   // operand staging buffers start as zeros (padding channels stay zero for the CTA's lifetime)
-  for (int i = tid; i < (K::oQS - K::oAX) / 16; i += kThreadsQ) reinterpret_cast<uint4*>(smem + K::oAX)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 128 * K::CP; i += kThreadsQ) {
+  for (int i = tid; i < (K::oQS - K::oAX) / 16; i += K::THREADS) reinterpret_cast<uint4*>(smem + K::oAX)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 128 * K::CP; i += K::THREADS) {
     const int hd = i / K::CP, c = i % K::CP, h = hd >> 5, d = hd & 31;
     const uint32_t off = h * (32 * K::CP * 4) + (d & 7) * 16 + (d >> 3) * K::A_SBO + (c >> 2) * 128 + (c & 3) * 4;
     const float wq = c < C ? a.wqkv[(size_t)hd * C + c] * kLog2e : 0.f;
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(kThreadsQ, 1) la_bwd_q_tc_kernel(LAArgs a) {
     *reinterpret_cast<uint32_t*>(smem + K::oBQ + off) = f2tf(wq);
     *reinterpret_cast<uint32_t*>(smem + K::oBG + off) = f2tf(gg);
   }
-  for (int i = tid; i < 4 * K::NC * 32; i += kThreadsQ) {
+  for (int i = tid; i < 4 * K::NC * 32; i += K::THREADS) {
     const int h = i / (K::NC * 32), rem = i % (K::NC * 32), c = rem >> 5, d = rem & 31;
     const float w = c < C ? a.wqkv[(size_t)(h * 32 + d) * C + c] * kTfBiasMul : 0.f;
     *reinterpret_cast<uint32_t*>(smem + K::oBW + h * (K::NC * 128) + (c & 7) * 16 + (c >> 3) * 1024 + (d >> 2) * 128 + (d & 3) * 4) = f2tf(w);
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(kThreadsQ, 1) la_bwd_q_tc_kernel(LAArgs a) {
       __syncwarp();
       if (lane == 0) { mbar_arrive(BAR(bDONE + h)); mbar_arrive(BAR(bTILE + (t & 1))); }
     }
-  } else if (warp >= kMmaWarp0) {
+  } else if (warp >= K::MMAW0) {
     // ------------------------------------------------------------------------------------------ MMA issue
     // Four issuing warps (a single thread cannot issue ~40 small MMAs per tile fast enough, and the score MMAs must
     // run ahead of the compute warps, never behind a wait for them): warps 20 / 21 the score MMAs of the even / odd
@@ -227,8 +234,8 @@ __global__ void __launch_bounds__(kThreadsQ, 1) la_bwd_q_tc_kernel(LAArgs a) {
     constexpr uint32_t id_x = make_idesc(kFmtTF32, 128, K::NC, 0, 0);
     constexpr uint32_t id_g = make_idesc(kFmtBF16, 128, K::NC, 1, 0);
     constexpr uint32_t hiA = (K::A_SBO >> 4) | (1u << 14), hiW = (1024u >> 4) | (1u << 14), hiT = (2048u >> 4) | (1u << 14);
-    if (warp <= kMmaWarp0 + 1) {
-      for (int s = warp - kMmaWarp0; s < S; s += 2) {   // Q' and dQs of step s into ring slot s % NREG
+    if (warp <= K::MMAW0 + 1) {
+      for (int s = warp - K::MMAW0; s < S; s += 2) {   // Q' and dQs of step s into ring slot s % NREG
         const int t = s >> 2, h = s & 3, reg = s % NREG, st = t % K::NSTG;
         mbar_wait(BAR(bFULL + st), (uint32_t)((t / K::NSTG) & 1), 20, wdbg, (uint32_t)(s));
         if (s >= NREG) mbar_wait(BAR(bLD + (s - NREG) % (2 * NREG)), (uint32_t)(((s - NREG) / (2 * NREG)) & 1), 21, wdbg, (uint32_t)(s));   // slot loaded by step s - 5
@@ -244,7 +251,7 @@ __global__ void __launch_bounds__(kThreadsQ, 1) la_bwd_q_tc_kernel(LAArgs a) {
         }
         __syncwarp();
       }
-    } else if (warp == kMmaWarp0 + 2) {
+    } else if (warp == K::MMAW0 + 2) {
       for (int t = 0; t < NT; ++t) {
         const int p = t & 1;
         if (t >= 2) mbar_wait(BAR(bDXNFREE + p), (uint32_t)(((t >> 1) - 1) & 1), 23, wdbg, (uint32_t)(t));   // accumulator of tile t - 2 drained
@@ -380,15 +387,15 @@ __global__ void __launch_bounds__(kThreadsQ, 1) la_bwd_q_tc_kernel(LAArgs a) {
         for (int c = 0; c < C; ++c) a.dxnq[((size_t)r * C + c) * a.L + n] = __uint_as_float(d[c]);
       }
     };
-    for (int t = set; t < K::NSTG && t < NT; t += kAuxSets) { load_tile(t); stage(t); }
+    for (int t = set; t < K::NSTG && t < NT; t += K::AUX) { load_tile(t); stage(t); }
     if (K::NSTG + set < NT) load_tile(K::NSTG + set);
-    for (int t = set; t < NT; t += kAuxSets) {
+    for (int t = set; t < NT; t += K::AUX) {
       if (t + K::NSTG < NT) {
         // stage buffer t % NSTG has been consumed (a barrier per buffer: its next phase needs this very staging, so a
         // slow staging warp can never miss a phase)
         mbar_wait(BAR(bSFREE + t % K::NSTG), (uint32_t)((t / K::NSTG) & 1), 31, wdbg, (uint32_t)(t));
         stage(t + K::NSTG);
-        if (t + K::NSTG + kAuxSets < NT) load_tile(t + K::NSTG + kAuxSets);     // in flight while this tile drains
+        if (t + K::NSTG + K::AUX < NT) load_tile(t + K::NSTG + K::AUX);     // in flight while this tile drains
       }
       drain(t);
     }
@@ -422,7 +429,7 @@ __global__ void __launch_bounds__(kThreadsQ, 1) la_bwd_q_tc_kernel(LAArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp0) tmem_dealloc(tm, 512);
+  if (warp == K::MMAW0) tmem_dealloc(tm, 512);
 #undef BAR
 }
 
@@ -433,7 +440,7 @@ static int launch_bwd_q(const LAArgs& a, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((unsigned)a.nchunk, (unsigned)a.R);
-  kern<<<grid, kThreadsQ, K::SMEM, st>>>(a);
+  kern<<<grid, K::THREADS, K::SMEM, st>>>(a);
   DQ_LAUNCH_CHECK();
   return 0;
 }
