@@ -452,7 +452,10 @@ __device__ __forceinline__ float cf_dsilu(float z) {
 // space-to-depth copy of x, no depth-to-space pass over dx, no weight re-packing (dq_s2d / dq_d2s / dq_down_w).
 template <int COUT, int K, int P, int NT, bool EPI, bool BULK, bool RES = false, int NCI = 0, bool UP2 = false,
           bool DOWN2 = false>
-__global__ void __launch_bounds__(NT) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs a) {
+#ifndef DQ_CB_MMA_MINB
+#define DQ_CB_MMA_MINB 1   // resident CTAs per SM asked of the tensor-core variants (measured: see DESIGN.md section 4)
+#endif
+__global__ void __launch_bounds__(NT, (NCI > 0 ? DQ_CB_MMA_MINB : 1)) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs a) {
   constexpr bool MMA = NCI > 0;
   static_assert(!MMA || (EPI && K == 3), "MMA variant: conv3 with epilogue");
   static_assert(!UP2 || (!EPI && !RES && !MMA && K == 3 && P >= 2), "UP2: plain conv3, FFMA contractions, pairs per thread");
