@@ -266,7 +266,7 @@ class DDIMDiffusionModel(ModelInterface):
         xT = torch.empty((chunk, rt, mz), dtype=torch.float32, device=dev)
         c2 = torch.empty_like(xT)
         c1 = torch.empty((chunk, rt), dtype=torch.float32, device=dev)
-        graph, res = None, None
+        graph, res, stage = None, None, None
         pending = []
         with torch.no_grad():
             for s in range(0, n, chunk):
@@ -292,8 +292,20 @@ class DDIMDiffusionModel(ModelInterface):
                     xt = torch.empty((nb, rt, mz), dtype=torch.float32, device=dev)
                     draw_xT(cid, xt)
                     x, pn = self.sample(xt, a.float().contiguous(), b1.float().contiguous(), num_steps=num_steps)
+                cur = torch.cuda.current_stream(dev)
+                if graph is not None and nb == chunk:
+                    # the graph's output buffers are overwritten by the next replay: move the results to staging buffers
+                    # (a device-to-device copy, ~0.1 ms) so that the next replay does not wait for the host copy
+                    if stage is None:
+                        stage = (torch.empty_like(xT), torch.empty_like(xT) if return_noise else None)
+                    if pending:
+                        cur.wait_event(pending[-1])          # the previous host copy has read the staging buffers
+                    stage[0].copy_(x)
+                    if return_noise:
+                        stage[1].copy_(pn)
+                    x, pn = stage
                 ev = torch.cuda.Event()
-                ev.record(torch.cuda.current_stream(dev))
+                ev.record(cur)
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(ev)
                     out[s:s + nb].copy_(x[:nb], non_blocking=True)
@@ -301,9 +313,6 @@ class DDIMDiffusionModel(ModelInterface):
                         out_noise[s:s + nb].copy_(pn[:nb], non_blocking=True)
                     done = torch.cuda.Event()
                     done.record(copy_stream)
-                if graph is not None:
-                    # the graph's output buffers are overwritten by the next replay: it must wait for this copy
-                    torch.cuda.current_stream(dev).wait_event(done)
                 pending.append(done)
         for e in pending:
             e.synchronize()
