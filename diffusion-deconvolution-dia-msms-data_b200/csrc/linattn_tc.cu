@@ -147,6 +147,15 @@ __global__ void __launch_bounds__(BQ<C>::THREADS, 1) la_bwd_q_tc_kernel(LAArgs a
   __syncthreads();
   tc_fence_after();
 
+  // Two staging sets = 28 warps compiled for 72 registers (pool 28 x 72 = 2016 per lane): the roles are re-balanced with
+  // setmaxnreg - compute warps 80, staging / draining warps 64, MMA-issuing warps 40 (16 x 80 + 8 x 64 + 4 x 40 = 1952 <=
+  // 2016; a request beyond the pool would block forever).  Measured at C = 8, L = 10000: backward 1.436 -> 1.395 ms;
+  // 88 / 56 / 40 is slower (the staging warps spill at 56)
+  if constexpr (K::AUX == 2) {
+    if (warp < 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
+    else if (warp < K::MMAW0) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  }
   if (warp < 16) {
     // ------------------------------------------------------------------------------------------ per-element math
     const int h = warp >> 2, quad = warp & 3;
