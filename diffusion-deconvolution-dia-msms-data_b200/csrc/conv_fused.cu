@@ -2363,7 +2363,7 @@ DQ_API int dq_upconv_bwd_fused(const float* dy, const float* x, const float* w, 
   cudaStream_t st = (cudaStream_t)stream;
   if (R <= 0 || Lh <= 0) return 0;
   if ((cin & 3) || cin > 64 || 2 * Lh < 128) return 1;
-  const bool al = (Lh % 4 == 0) && ((((size_t)dy | (size_t)x) & 15) == 0);
+  const bool al = (Lh % 4 == 0) && ((((size_t)dy | (size_t)x | (size_t)dx) & 15) == 0);
   switch (cout) {
     case 4: return al ? launch_fused_tma<4, 3, 4, 128, false, true, false, 0, true>(a, st)
                       : launch_fused_tma<4, 3, 4, 128, false, false, false, 0, true>(a, st);
