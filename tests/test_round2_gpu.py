@@ -404,3 +404,55 @@ def test_init_conv_forward_pipelined_kernel_vs_torch(L, rt):
     ref = torch.nn.functional.conv1d(torch.cat([cond * sc + sh, x], 1), net._w("init_conv.weight").view(cout, 2, 7),
                                      net._w("init_conv.bias"), padding=3)
     assert rel_err(y, ref) < 1e-5, rel_err(y, ref)
+
+
+def _misaligned(t):
+    """A contiguous copy of `t` whose base address is 4 bytes past a 16-byte boundary (kernels must leave their vector paths)."""
+    flat = torch.empty(t.numel() + 1, dtype=t.dtype, device=t.device)
+    v = flat[1:].view(t.shape)
+    v.copy_(t)
+    assert v.is_contiguous() and v.data_ptr() % 16 == 4
+    return v
+
+
+def test_resampling_kernels_accept_tensors_that_are_not_16_byte_aligned():
+    """One-pass Upsample / Downsample backward and the pipelined Downsample / init_conv forward on tensors whose base
+    pointers are only 4-byte aligned (views into larger buffers): same results as on aligned copies."""
+    net, _ = make_net(seed=9)
+    net._ensure_grads()
+    R, L = 3, 512
+    g = torch.Generator(device="cuda").manual_seed(5)
+    # Upsample backward (ups.2: 12 -> 12 channels in the default net)
+    wn, bn = "ups.2.3.1.weight", "ups.2.3.1.bias"
+    cout, cin, _ = net.specs[wn]
+    x = torch.randn(R, cin, L // 2, device="cuda", generator=g)
+    du = torch.randn(R, cout, L, device="cuda", generator=g)
+    res = []
+    for f in (lambda t: t, _misaligned):
+        net.zero_grad()
+        dx = net._upconv_bwd(f(du), f(x), wn, bn, True, None, 1)
+        res.append((dx.clone(), net._gw(wn).clone(), net._gw(bn).clone()))
+    for a, b in zip(*res):
+        assert rel_err(b, a) < 1e-5
+    # Downsample backward and forward (downs.2: 8 -> 8)
+    wn, bn = "downs.2.3.weight", "downs.2.3.bias"
+    cout, cin, _ = net.specs[wn]
+    x = torch.randn(R, cin, L, device="cuda", generator=g)
+    du = torch.randn(R, cout, L // 2, device="cuda", generator=g)
+    res = []
+    for f in (lambda t: t, _misaligned):
+        net.zero_grad()
+        dx = net._downconv_bwd(f(du), f(x), wn, bn, True, None, 1)
+        y, _ = net._conv_fwd(f(x), None, wn, bn, 4, 2, 1, 1, L // 2)
+        res.append((dx.clone(), net._gw(wn).clone(), net._gw(bn).clone(), y.clone()))
+    for a, b in zip(*res):
+        assert rel_err(b, a) < 1e-5
+    # init_conv forward
+    b_, rt = 1, 3
+    net._time_path_fwd(torch.tensor([11], device="cuda"), b_, False)
+    ico = net.ss_off["init_cond_proj.to_scale_shift.1"]
+    cond = torch.randn(rt, 1, L, device="cuda", generator=g)
+    xx = torch.randn(rt, 1, L, device="cuda", generator=g)
+    ys = [net._conv_fwd(f(cond), f(xx), "init_conv.weight", "init_conv.bias", 7, 1, 3, 1, L, in_ss=ico, rps=rt)[0].clone()
+          for f in (lambda t: t, _misaligned)]
+    assert rel_err(ys[1], ys[0]) < 1e-6
