@@ -452,10 +452,12 @@ __device__ __forceinline__ float cf_dsilu(float z) {
 // space-to-depth copy of x, no depth-to-space pass over dx, no weight re-packing (dq_s2d / dq_d2s / dq_down_w).
 template <int COUT, int K, int P, int NT, bool EPI, bool BULK, bool RES = false, int NCI = 0, bool UP2 = false,
           bool DOWN2 = false>
-#ifndef DQ_CB_MMA_MINB
-#define DQ_CB_MMA_MINB 1   // resident CTAs per SM asked of the tensor-core variants (measured: see DESIGN.md section 4)
-#endif
-__global__ void __launch_bounds__(NT, (NCI > 0 ? DQ_CB_MMA_MINB : 1)) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs a) {
+// (no minimum-blocks argument: an explicit `1` makes ptxas spend 152 instead of 128 registers on the 4-channel variants -
+// three instead of four resident CTAs, level-0 ResnetBlock backward 1362 -> 1495 us; asking for three CTAs of the
+// tensor-core variants changes nothing at 8 channels and spills at 12 / 16)
+// (the 4-channel res_conv variant is the exception: shared memory limits it to two CTAs anyway, and with the explicit `1`
+// it keeps 161 registers instead of spilling at 128: 2131 -> 2046 us at level 0; 0 = no request)
+__global__ void __launch_bounds__(NT, (RES && NCI == 0 && COUT == 4) ? 1 : 0) conv_bwd_fused_tma_kernel(ConvBwdFusedArgs a) {
   constexpr bool MMA = NCI > 0;
   static_assert(!MMA || (EPI && K == 3), "MMA variant: conv3 with epilogue");
   static_assert(!UP2 || (!EPI && !RES && !MMA && K == 3 && P >= 2), "UP2: plain conv3, FFMA contractions, pairs per thread");
