@@ -46,6 +46,9 @@ struct TC {
 #ifndef LA_KV_ASYNC_MAXC
 #define LA_KV_ASYNC_MAXC 4  // k / v backward: epilogue inputs and the next x tile prefetched by cp.async up to this C
 #endif
+#ifndef LA_OCCBIG
+#define LA_OCCBIG 1  // the same for C = 12 / 16 (0 = no request)
+#endif
 #ifndef LA_OCC8
 #define LA_OCC8 4  // resident CTAs per SM asked of the C = 8 backward kernels
 #endif
@@ -631,7 +634,7 @@ __global__ void __launch_bounds__(128) la_out_kernel(LAArgs a) {
 // Reductions over positions (Gq = Qs^T dY, dWq = dQr^T Xn) read Qs / dQr back from warp-private shared tiles in
 // the transposed role.
 template <int C>
-__global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? LA_OCC8 : 1))) la_bwd_q_kernel(LAArgs a) {
+__global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? LA_OCC8 : LA_OCCBIG))) la_bwd_q_kernel(LAArgs a) {
   using T = TC<C>;
   extern __shared__ float4 dyn_smem4[];
   // C = 4: ONE [pos][8] tile with xn and dy interleaved (xn0, dy0, xn1, dy1, ..): a single A fragment then carries xn
@@ -953,7 +956,7 @@ __global__ void __launch_bounds__(128) la_bwd_combine_kernel(LAArgs a, int rows_
 
 // ------------------------------------------------------------------------------------------- backward: k path
 template <int C>
-__global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? LA_OCC8 : 1))) la_bwd_kv_kernel(LAArgs a) {
+__global__ void __launch_bounds__(128, (C <= 4 ? LA_OCC4 : (C <= 8 ? LA_OCC8 : LA_OCCBIG))) la_bwd_kv_kernel(LAArgs a) {
   using T = TC<C>;
   extern __shared__ float4 dyn_smem4[];
   float* xn_s = reinterpret_cast<float*>(dyn_smem4);   // TA<C>::SIZE (natural A-operand layout)
