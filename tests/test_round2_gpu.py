@@ -456,3 +456,17 @@ def test_resampling_kernels_accept_tensors_that_are_not_16_byte_aligned():
     ys = [net._conv_fwd(f(cond), f(xx), "init_conv.weight", "init_conv.bias", 7, 1, 3, 1, L, in_ss=ico, rps=rt)[0].clone()
           for f in (lambda t: t, _misaligned)]
     assert rel_err(ys[1], ys[0]) < 1e-6
+
+
+@pytest.mark.parametrize("rows,cols", [(300, 514), (256, 10000), (10000, 128), (64, 64), (33, 65), (2, 2)])
+def test_cast_transpose_matches_torch_bit_exactly(rows, cols):
+    """dq_cast_transpose (bf16 operand refresh of the mid-stage weights after AdamW): both layouts equal torch's
+    round-to-nearest-even casts bit for bit, through the packed 64 x 64 kernel (even shapes) and the 32 x 32 one."""
+    from dquartic import _native as N
+    g = torch.Generator(device="cuda").manual_seed(rows * 31 + cols)
+    x = torch.randn(rows, cols, device="cuda", generator=g)
+    out = torch.empty(rows, cols, dtype=torch.bfloat16, device="cuda")
+    out_t = torch.empty(cols, rows, dtype=torch.bfloat16, device="cuda")
+    N.call("dq_cast_transpose", x, out, out_t, rows, cols)
+    assert torch.equal(out, x.bfloat16())
+    assert torch.equal(out_t, x.t().contiguous().bfloat16())

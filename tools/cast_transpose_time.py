@@ -1,0 +1,13 @@
+import torch, sys
+sys.path.insert(0, "/root/repo/diffusion-deconvolution-dia-msms-data_b200")
+from dquartic import _native as N
+x = torch.randn(10000, 10000, device="cuda")
+o = torch.empty(10000, 10000, dtype=torch.bfloat16, device="cuda"); ot = torch.empty_like(o)
+for _ in range(3): N.call("dq_cast_transpose", x, o, ot, 10000, 10000)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20): N.call("dq_cast_transpose", x, o, ot, 10000, 10000)
+e1.record(); torch.cuda.synchronize()
+t = e0.elapsed_time(e1) / 20
+print(f"cast_transpose 10000x10000: {t*1000:.0f} us = {0.8e9/t/1e9*1e3/1e3:.2f} TB/s")
