@@ -49,6 +49,35 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16
   }
 }
 
+// The same on 64 x 64 tiles with packed bf16x2 loads and stores (rows, cols, ld_out even; 4-byte aligned bases): the
+// 32 x 32 version above moved 2 bytes per thread and access (1.6 TB/s on the 2304 x 10000 activation transposes).
+__global__ void __launch_bounds__(256) transpose_bf16_64_kernel(const __nv_bfloat16* __restrict__ in,
+                                                                __nv_bfloat16* __restrict__ out, int rows, int cols,
+                                                                long ld_out, int row_shift) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+  for (int i = ty; i < 64; i += 8) {
+    const int r = r0 + i + row_shift, c = c0 + 2 * tx;
+    __nv_bfloat162 v = zero2;
+    if (r >= 0 && r < rows && c < cols) v = *reinterpret_cast<const __nv_bfloat162*>(in + (size_t)r * cols + c);
+    *reinterpret_cast<__nv_bfloat162*>(&tile[i][2 * tx]) = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = ty; i < 64; i += 8) {
+    const int c = c0 + i, r = r0 + 2 * tx;
+    if (c < cols && r < rows) {
+      __nv_bfloat162 v;
+      v.x = tile[2 * tx][i];
+      v.y = tile[2 * tx + 1][i];
+      *reinterpret_cast<__nv_bfloat162*>(out + (size_t)c * ld_out + r) = v;
+    }
+  }
+}
+
 // fp32 [rows][cols] -> bf16 [rows][cols] and/or bf16 transposed [cols][rows]   (weight refresh after AdamW)
 __global__ void __launch_bounds__(256) cast_transpose_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                              __nv_bfloat16* __restrict__ out_t, int rows, int cols) {
@@ -410,6 +439,12 @@ DQ_API int dq_mid_pack(const float* x, void* out_bf16, int b, int rt, int N, int
 }
 DQ_API int dq_transpose_bf16(const void* in, void* out, int rows, int cols, long ld_out, int row_shift, void* stream) {
   if (rows <= 0 || cols <= 0) return 0;
+  if (((rows | cols) & 1) == 0 && (ld_out & 1) == 0 && (((size_t)in | (size_t)out) & 3) == 0) {
+    dim3 grid64((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64));
+    transpose_bf16_64_kernel<<<grid64, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, rows, cols, ld_out, row_shift);
+    DQ_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
   transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, rows, cols, ld_out, row_shift);
   DQ_LAUNCH_CHECK();

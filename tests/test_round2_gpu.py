@@ -470,3 +470,20 @@ def test_cast_transpose_matches_torch_bit_exactly(rows, cols):
     N.call("dq_cast_transpose", x, out, out_t, rows, cols)
     assert torch.equal(out, x.bfloat16())
     assert torch.equal(out_t, x.t().contiguous().bfloat16())
+
+
+@pytest.mark.parametrize("rows,cols,ld,shift", [(72, 10000, 80, 0), (72, 10000, 80, -1), (72, 10000, 80, 1), (2304, 256, 2304, 0),
+                                                (70, 130, 72, 1), (33, 65, 40, 0), (64, 64, 64, -1)])
+def test_transpose_bf16_with_row_shift_matches_torch(rows, cols, ld, shift):
+    """dq_transpose_bf16: out[c][r] = in[r + shift][c] (zero outside), leading dimension ld - the activation transposes of
+    the mid-stage weight-gradient GEMMs, through the packed 64 x 64 kernel (even shapes) and the 32 x 32 one."""
+    from dquartic import _native as N
+    g = torch.Generator(device="cuda").manual_seed(rows + cols + shift)
+    x = torch.randn(rows, cols, device="cuda", generator=g).bfloat16()
+    out = torch.full((cols, ld), 7.0, dtype=torch.bfloat16, device="cuda")
+    N.call("dq_transpose_bf16", x, out, rows, cols, ld, shift)
+    ref = torch.zeros(rows, cols, dtype=torch.bfloat16, device="cuda")
+    lo, hi = max(0, -shift), min(rows, rows - shift)
+    ref[lo:hi] = x[lo + shift:hi + shift]
+    assert torch.equal(out[:, :rows], ref.t())
+    assert bool((out[:, rows:] == 7.0).all())       # the padding columns of the destination are left alone
