@@ -138,6 +138,85 @@ struct RowNormArgs {
   int b, rt, N, upad, opad, ss_stride, act;
 };
 
+// 16-byte vector version (N a multiple of 4, every base pointer 16-byte aligned - 8 bytes for the bf16 output): one row per
+// CTA, the row stays in registers between the norm pass and the apply pass when it fits (N <= 10240: the 10000-channel
+// mid stage), so u is read once; float4 loads of g / scale / shift / residual, float4 + 8-byte bf16x4 stores.  Same
+// arithmetic per element as rownorm_fwd_kernel; the sum of squares is accumulated in a different order.
+__global__ void __launch_bounds__(256) rownorm_fwd4_kernel(RowNormArgs a) {
+  __shared__ float red[8];
+  constexpr int KEEP = 10;
+  const int m = blockIdx.x, tid = threadIdx.x;
+  const int s = m / a.rt;
+  const int nv = a.N >> 2;
+  const float4* u4 = reinterpret_cast<const float4*>(a.u + (size_t)padded_row(m, a.rt, a.upad) * a.N);
+  const bool keep = nv <= KEEP * 256;
+  float4 buf[KEEP];
+  float sc = 1.f;
+  if (a.g) {
+    float s2 = 0.f;
+    if (keep) {
+#pragma unroll
+      for (int k = 0; k < KEEP; ++k) {
+        const int i = tid + k * 256;
+        buf[k] = i < nv ? u4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        s2 = fmaf(buf[k].x, buf[k].x, fmaf(buf[k].y, buf[k].y, fmaf(buf[k].z, buf[k].z, fmaf(buf[k].w, buf[k].w, s2))));
+      }
+    } else {
+      for (int i = tid; i < nv; i += 256) {
+        const float4 v = u4[i];
+        s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+      }
+    }
+    s2 = warp_sum(s2);
+    if ((tid & 31) == 0) red[tid >> 5] = s2;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
+    if (a.inv_out && tid == 0) a.inv_out[m] = inv;
+    sc = inv * sqrtf((float)a.N);
+  } else if (keep) {
+#pragma unroll
+    for (int k = 0; k < KEEP; ++k) {
+      const int i = tid + k * 256;
+      buf[k] = i < nv ? u4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float4* g4 = a.g ? reinterpret_cast<const float4*>(a.g) : nullptr;
+  // (the scale / shift columns of a producer start at an even, not necessarily 4-aligned column of SS: 8-byte loads)
+  const float2* sc2 = a.ss ? reinterpret_cast<const float2*>(a.ss + (size_t)s * a.ss_stride) : nullptr;
+  const float2* sh2 = a.ss ? reinterpret_cast<const float2*>(a.ss + (size_t)s * a.ss_stride + a.N) : nullptr;
+  const float4* r4 = a.res ? reinterpret_cast<const float4*>(a.res + (size_t)m * a.N) : nullptr;
+  float4* of4 = a.out_f32 ? reinterpret_cast<float4*>(a.out_f32 + (size_t)m * a.N) : nullptr;
+  uint2* ob4 = a.out_bf16 ? reinterpret_cast<uint2*>(a.out_bf16 + (size_t)padded_row(m, a.rt, a.opad) * a.N) : nullptr;
+  auto apply = [&](float4 v, int i) {
+    float z[4] = {v.x, v.y, v.z, v.w};
+    if (g4) { const float4 gg = g4[i]; z[0] = z[0] * sc * gg.x; z[1] = z[1] * sc * gg.y; z[2] = z[2] * sc * gg.z; z[3] = z[3] * sc * gg.w; }
+    if (sc2) {
+      const float2 a0 = sc2[2 * i], a1 = sc2[2 * i + 1], b0 = sh2[2 * i], b1 = sh2[2 * i + 1];
+      z[0] = fmaf(z[0], a0.x + 1.f, b0.x); z[1] = fmaf(z[1], a0.y + 1.f, b0.y);
+      z[2] = fmaf(z[2], a1.x + 1.f, b1.x); z[3] = fmaf(z[3], a1.y + 1.f, b1.y);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z[j] = act_fwd(z[j], a.act);
+    if (r4) { const float4 rr = r4[i]; z[0] += rr.x; z[1] += rr.y; z[2] += rr.z; z[3] += rr.w; }
+    if (of4) of4[i] = make_float4(z[0], z[1], z[2], z[3]);
+    if (ob4) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(z[0], z[1]), hi = __floats2bfloat162_rn(z[2], z[3]);
+      ob4[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+    }
+  };
+  if (keep) {
+#pragma unroll
+    for (int k = 0; k < KEEP; ++k) {
+      const int i = tid + k * 256;
+      if (i < nv) apply(buf[k], i);
+    }
+  } else {
+    for (int i = tid; i < nv; i += 256) apply(u4[i], i);
+  }
+}
+
 __global__ void __launch_bounds__(256) rownorm_fwd_kernel(RowNormArgs a) {
   __shared__ float red[8];
   const int m = blockIdx.x;
@@ -468,6 +547,12 @@ DQ_API int dq_rownorm_fwd(const float* u, int upad, const float* g, const float*
                           int N, void* stream) {
   if (b <= 0) return 0;
   RowNormArgs a{u, g, ss, res, out_f32, (__nv_bfloat16*)out_bf16, inv_out, b, rt, N, upad, opad, ss_stride, act};
+  const size_t al = (size_t)u | (size_t)g | (size_t)res | (size_t)out_f32;
+  if ((N & 3) == 0 && (al & 15) == 0 && (((size_t)out_bf16 | (size_t)ss) & 7) == 0 && (!ss || (ss_stride & 1) == 0)) {
+    rownorm_fwd4_kernel<<<(unsigned)(b * rt), 256, 0, (cudaStream_t)stream>>>(a);
+    DQ_LAUNCH_CHECK();
+    return 0;
+  }
   rownorm_fwd_kernel<<<(unsigned)(b * rt), 256, 0, (cudaStream_t)stream>>>(a);
   DQ_LAUNCH_CHECK();
   return 0;

@@ -487,3 +487,38 @@ def test_transpose_bf16_with_row_shift_matches_torch(rows, cols, ld, shift):
     ref[lo:hi] = x[lo + shift:hi + shift]
     assert torch.equal(out[:, :rows], ref.t())
     assert bool((out[:, rows:] == 7.0).all())       # the padding columns of the destination are left alone
+
+
+@pytest.mark.parametrize("N,act,with_ss,with_res", [(10000, 1, True, False), (10000, 1, False, True), (20000, 1, True, True),
+                                                    (520, 0, False, False), (1002, 1, True, True)])
+def test_rownorm_forward_vector_and_scalar_kernels_vs_torch(N, act, with_ss, with_res):
+    """dq_rownorm_fwd (RMSNorm(10000) + per-sample scale/shift + SiLU + residual of the mid stage, reference
+    unet1d.py:126-140, 260-266) against torch: the 16-byte vector kernel (N % 4 == 0; the row kept in registers for N <=
+    10240, re-read above) and the scalar kernel (N = 1002), fp32 and bf16 outputs."""
+    from dquartic import _native as N_
+    b, rt = 3, 5
+    M = b * rt
+    gen = torch.Generator(device="cuda").manual_seed(N + act)
+    u = torch.randn(M, N, device="cuda", generator=gen)
+    g = torch.rand(N, device="cuda", generator=gen) + 0.5
+    ssw = 2 * N + 6                       # scale | shift of this producer start at column 2 of a wider SS buffer
+    SS = torch.randn(b, ssw, device="cuda", generator=gen) * 0.3
+    res = torch.randn(M, N, device="cuda", generator=gen) if with_res else None
+    of = torch.empty(M, N, device="cuda")
+    ob = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    inv = torch.empty(M, device="cuda")
+    ssp = SS.data_ptr() + 8 if with_ss else None
+    N_.call("dq_rownorm_fwd", u, 0, g, ssp, ssw, act, res, of, ob, 0, inv, b, rt, N)
+    nrm = u.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    z = u / nrm * g * (N ** 0.5)
+    if with_ss:
+        sc = SS[:, 2:2 + N].repeat_interleave(rt, 0)
+        sh = SS[:, 2 + N:2 + 2 * N].repeat_interleave(rt, 0)
+        z = z * (sc + 1) + sh
+    if act == 1:
+        z = torch.nn.functional.silu(z)
+    if with_res:
+        z = z + res
+    assert rel_err(of, z) < 2e-6
+    assert rel_err(ob.float(), z.bfloat16().float()) < 1e-2 and float((ob.float() - z).abs().max()) < 0.05 * float(z.abs().max())
+    assert rel_err(inv, (1.0 / nrm).flatten()) < 1e-6
