@@ -1,5 +1,6 @@
-import torch, sys
-sys.path.insert(0, "/root/repo/diffusion-deconvolution-dia-msms-data_b200")
+"""Timing of dq_cast_transpose (bf16 operand refresh) on one 10000 x 10000 tap: python tools/cast_transpose_time.py"""
+import torch, sys, os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "diffusion-deconvolution-dia-msms-data_b200"))
 from dquartic import _native as N
 x = torch.randn(10000, 10000, device="cuda")
 o = torch.empty(10000, 10000, dtype=torch.bfloat16, device="cuda"); ot = torch.empty_like(o)
